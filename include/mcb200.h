@@ -1,0 +1,243 @@
+/******************************************************************************
+ * mcb200.h - C ABI of the B200-native MetaCache query hot path (libmcb200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * It is what a maintainer binds underneath the reference's GPU seam
+ * (`database.hpp:183-189`: feature_store = gpu_hashmap<>, result_handler =
+ * query_batch<>).  Each entry point cites the reference interface it replaces.
+ * C++ shims with the reference's class/member names live in
+ * metacache_b200/host/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every int-returning function returns 0 on success (or a count where
+ *     documented) and a negative MCB200_E* code on failure; the message is
+ *     available from mcb200_last_error() (thread local).  The library never
+ *     calls exit() (the reference's CUERR does, cuda_helpers.cuh:18-25).
+ *   - locations are u64 = (tgt << 32) | win, i.e. exactly the 8 on-disk bytes
+ *     of `database::location{win,tgt}` read as one little-endian u64
+ *     (database.hpp:136-166); u64 '<' is location::operator<.
+ *   - the library owns all pinned-host and device memory it hands out; result
+ *     pointers stay valid until the slot is cleared or resubmitted.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with MCB200_ENODEVICE.
+ *****************************************************************************/
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_ABI_VERSION 1
+
+enum {
+    MCB200_OK        =  0,
+    MCB200_EINVAL    = -1,   /* bad argument / unsupported parameter value   */
+    MCB200_ENODEVICE = -2,   /* no usable CUDA device                        */
+    MCB200_ECUDA     = -3,   /* CUDA runtime error (message has the details) */
+    MCB200_ENOMEM    = -4,
+    MCB200_EIO       = -5,   /* database file could not be read              */
+    MCB200_ESTATE    = -6    /* call order violated                          */
+};
+
+/* hash_dna.hpp:99-163 sketching_options {kmerlen, sketchlen, winlen, winstride}.
+ * Supported: 1 <= kmerlen <= 16 (32-bit k-mers, config.hpp:45-60),
+ * 1 <= sketchlen <= 32, kmerlen <= winlen <= 4096, winstride >= 1.          */
+typedef struct mcb200_sketching {
+    uint32_t kmerlen, sketchlen, winlen, winstride;
+} mcb200_sketching;
+
+/* candidate_structs.hpp:80-104 match_candidate minus the host-only `tax`
+ * pointer (the C++ shim fills it from its lineage cache).  Unused entries:
+ * tgt = 0xFFFFFFFF, hits = 0 (query_batch.cuh:212-259).                      */
+typedef struct mcb200_candidate {
+    uint32_t tgt, hits, beg, end;
+} mcb200_candidate;
+
+typedef struct mcb200_db    mcb200_db;
+typedef struct mcb200_batch mcb200_batch;
+
+/* ---- library ----------------------------------------------------------- */
+int          mcb200_abi_version (void);
+const char*  mcb200_last_error  (void);
+int          mcb200_device_count (void);
+
+/* ---- feature store: replaces gpu_hashmap<feature,location>'s query half
+ *      (gpu_hashmap.cuh:131-311; gpu_hashmap.cu:637-920 query_hash_table) -- */
+
+/* prepare_query_tables(numParts, replication) (gpu_hashmap.cu:1320-1362):
+ * a store with n_parts read-only tables resident on CUDA device `device`.    */
+mcb200_db*   mcb200_db_open  (int device, uint32_t n_parts);
+void         mcb200_db_close (mcb200_db* db);
+
+/* read_binary(istream&, store&, part_id, progress) (gpu_hashmap.cu:813-912):
+ * streamable load of one part in `.cache` batch order
+ * (hash_multimap.hpp:1037-1082): begin(nkeys,nvalues) -> append(batch)* ->
+ * finish.  `values` are locations as stored on disk ({u32 win,u32 tgt} pairs
+ * == u64 (tgt<<32)|win).  Host pointers.  max_load_factor <= 0 selects the
+ * default (0.5; gpu_hashmap.cuh max_load_factor()).                          */
+int mcb200_db_part_begin  (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues,
+                           float max_load_factor);
+int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,
+                           const uint8_t* sizes, const uint64_t* values,
+                           uint64_t nkeys, uint64_t nvalues);
+/* same, arrays already in device memory on the store's device */
+int mcb200_db_part_append_device (mcb200_db* db, uint32_t part, const uint32_t* d_keys,
+                                  const uint8_t* d_sizes, const uint64_t* d_values,
+                                  uint64_t nkeys, uint64_t nvalues);
+int mcb200_db_part_finish (mcb200_db* db, uint32_t part);
+/* convenience: database::read_cache (database.cpp:167-179) for `<db>.cache<N>` */
+int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const char* path,
+                               float max_load_factor);
+
+/* copy_target_lineages_to_gpus (gpu_hashmap.cuh) reduced to what candidate
+ * generation needs: one opaque non-zero taxon key per target at the
+ * `-lowest` rank (0 = no ancestor at that rank: candidate dropped,
+ * candidate_generation.hpp:184-191).  NULL/0 restores rank "sequence".       */
+int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax_of_target, uint32_t n_targets);
+
+uint32_t mcb200_db_part_count   (const mcb200_db* db);               /* table_count()  */
+uint64_t mcb200_db_key_count    (const mcb200_db* db, uint32_t part); /* key_count()    */
+uint64_t mcb200_db_value_count  (const mcb200_db* db, uint32_t part); /* value_count()  */
+uint64_t mcb200_db_bucket_count (const mcb200_db* db, uint32_t part); /* bucket_count() = slots */
+uint64_t mcb200_db_device_bytes (const mcb200_db* db, uint32_t part);
+int      mcb200_db_device       (const mcb200_db* db);
+/* max_supported_locations_per_feature() (gpu_hashmap.cuh): 254 */
+uint32_t mcb200_max_supported_locations_per_feature (void);
+
+/* Build one part on the device from target sequences (row N4, minimal:
+ * sketch every target window exactly like `add_target`
+ * (host_hashmap.hpp:570-604), group by feature in (tgt,win) order, keep the
+ * first max_locations per feature).  `bases`/`seq_offsets` are DEVICE
+ * pointers: ASCII bases of n_targets sequences, sequence i = bases[off[i]..
+ * off[i+1]).  Target ids are first_target_id + i.  Used by bench.py to make
+ * the synthetic databases; checked against the reference's `metacache build`
+ * in tests.  out_windows (host, n_targets, may be NULL) receives the window
+ * count of each target (taxon::file_source::windows).                        */
+int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
+                                       const char* d_bases, const uint64_t* d_seq_offsets,
+                                       uint32_t n_targets, uint32_t first_target_id,
+                                       const mcb200_sketching* sk, uint32_t max_locations,
+                                       float max_load_factor, uint32_t* out_windows);
+/* Export a part back to `.cache` order (host arrays sized key_count /
+ * value_count): serialize (hash_multimap.hpp:1037-1082).                      */
+int mcb200_db_part_export (const mcb200_db* db, uint32_t part, uint32_t* keys,
+                           uint8_t* sizes, uint64_t* values);
+
+/* ---- query batch: replaces query_batch<location> (query_batch.cuh:346-423,
+ *      query_batch.cu:415-658) and gpu_hashmap::query_async
+ *      (gpu_hashmap.cu:1299-1313) ---------------------------------------- */
+
+/* query_batch(maxQueries, maxEncodeLength, maxSketchSize, maxResultsPerWindow,
+ *             maxCandidatesPerQuery, copyAllHits, numHostThreads, numGPUs, ..)
+ * n_slots = numHostThreads: each host thread owns one slot (hostId).         */
+mcb200_batch* mcb200_batch_create  (mcb200_db* db, uint32_t max_queries, uint64_t max_bases,
+                                    uint32_t max_candidates, int copy_all_hits, uint32_t n_slots);
+void          mcb200_batch_destroy (mcb200_batch* b);
+
+/* add_paired_read(hostId, seq1, seq2, sketching, rules) (query_batch.cuh:85-186).
+ * Returns 1 if added, 0 if the slot is full (nothing added), <0 on error.
+ * max_windows_in_range = candidate_generation_rules::maxWindowsInRange
+ * (candidate_structs.hpp:134-151).  len2 = 0 for unpaired reads.             */
+int mcb200_batch_add_read (mcb200_batch* b, uint32_t slot, const char* seq1, uint64_t len1,
+                           const char* seq2, uint64_t len2, uint32_t max_windows_in_range);
+/* Bulk form of the same: n_queries reads whose bases are concatenated in
+ * `bases` (host), sequence j = bases[offsets[j]..offsets[j+1]); paired != 0
+ * means sequences 2i,2i+1 are the mates of query i.  max_windows_in_range is
+ * computed per query as make_candidate_generation_rules does, from
+ * insert_size_max and winstride.  Returns number of queries added.           */
+int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const char* bases,
+                                const uint64_t* offsets, uint32_t n_queries, int paired,
+                                uint64_t insert_size_max, uint32_t winstride);
+
+/* database::query_gpu_async -> gpu_hashmap::query_async (asynchronous):
+ * H2D copy, encode, sketch, probe + candidate generation on every part,
+ * part-ordered merge, D2H copy of the results - all on the slot's stream.    */
+int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200_sketching* sk);
+/* query_host_data::wait_for_results (query_batch.cu:147)                     */
+int mcb200_batch_wait   (mcb200_batch* b, uint32_t slot);
+/* query_host_data::clear()                                                   */
+int mcb200_batch_clear  (mcb200_batch* b, uint32_t slot);
+
+uint32_t mcb200_batch_num_queries (const mcb200_batch* b, uint32_t slot);
+uint32_t mcb200_batch_num_windows (const mcb200_batch* b, uint32_t slot);
+/* top_candidates(i): max_candidates entries, best first                      */
+const mcb200_candidate* mcb200_batch_top_candidates (const mcb200_batch* b, uint32_t slot,
+                                                     uint32_t query);
+/* allhits(i): sorted per part, parts concatenated (host_hashmap.hpp:695-723);
+ * NULL/0 unless the batch was created with copy_all_hits.                    */
+const uint64_t* mcb200_batch_allhits (const mcb200_batch* b, uint32_t slot, uint32_t query,
+                                      uint64_t* n);
+/* per-window sketches of the last submit (for stage-level parity tests):
+ * window w of the slot (windows of query i are contiguous, mate 1 first);
+ * returns pointer to `sketchlen` features, *n = valid count, ascending.      */
+const uint32_t* mcb200_batch_sketch (const mcb200_batch* b, uint32_t slot, uint32_t window,
+                                     uint32_t* n);
+/* first window index of query i (num_queries+1 valid entries)                */
+uint32_t mcb200_batch_query_window_offset (const mcb200_batch* b, uint32_t slot, uint32_t query);
+/* device time of the last completed submit on this slot, CUDA events on the
+ * slot's stream: total (H2D..D2H) and kernels only; milliseconds             */
+int mcb200_batch_last_timing (const mcb200_batch* b, uint32_t slot, float* total_ms,
+                              float* kernels_ms);
+
+/* ---- device-resident pipeline (inputs/outputs already in HBM) ------------
+ * Same computation as submit, with caller-owned device buffers and stream
+ * (cudaStream_t passed as void*); used by bench.py's `value` measurement, by
+ * the multi-GPU driver (one process per GPU), and by the kernel-level tests. */
+typedef struct mcb200_dev_queries {
+    const char*     bases;         /* ASCII, n_bases bytes (+ readable 64 B tail pad) */
+    const uint32_t* seq_offsets;   /* n_seqs+1                                         */
+    const uint32_t* seq_query;     /* n_seqs: owning query of each sequence, ascending */
+    const uint32_t* max_win;       /* n_queries: maxWindowsInRange                     */
+    uint32_t        n_seqs;
+    uint32_t        n_queries;
+    uint64_t        n_bases;
+} mcb200_dev_queries;
+
+typedef struct mcb200_workspace mcb200_workspace;
+/* scratch for up to max_queries / max_seqs / max_bases per call               */
+mcb200_workspace* mcb200_workspace_create  (mcb200_db* db, uint32_t max_queries, uint32_t max_seqs,
+                                            uint64_t max_bases, uint32_t max_candidates,
+                                            int want_all_hits);
+void              mcb200_workspace_destroy (mcb200_workspace* ws);
+
+/* stage 1+2: encode + sketch.  After it: workspace holds window tables and
+ * sketches (see getters).                                                    */
+int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                          const mcb200_sketching* sk, void* stream);
+/* stage 3+4 for ONE part: probe + sort + contiguous-window candidates ->
+ * d_top[n_queries][max_candidates] (device).                                  */
+int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
+                              void* stream);
+/* stable part-ordered merge of n_lists candidate lists:
+ * d_parts[n_lists][n_queries][max_candidates] -> d_out[n_queries][max_candidates]
+ * (mode_merge.cpp:158-240 / candidate_generation.hpp:172-231 re-insert).     */
+int mcb200_merge_candidates_device (mcb200_workspace* ws, const mcb200_candidate* d_parts,
+                                    uint32_t n_lists, uint32_t n_queries, mcb200_candidate* d_out,
+                                    void* stream);
+/* whole pipeline over all parts of the store: sketch -> per part query ->
+ * merge -> d_top.                                                            */
+int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                         const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream);
+
+/* workspace introspection (device pointers, valid after the calls above)     */
+uint32_t        mcb200_workspace_num_windows   (const mcb200_workspace* ws);   /* syncs */
+const uint32_t* mcb200_workspace_sketches      (const mcb200_workspace* ws);   /* [nwin][sketchlen] */
+const uint32_t* mcb200_workspace_query_windows (const mcb200_workspace* ws);   /* [n_queries+1] */
+const uint64_t* mcb200_workspace_allhits       (const mcb200_workspace* ws);   /* concatenated */
+const uint64_t* mcb200_workspace_allhits_offsets (const mcb200_workspace* ws); /* [n_queries*parts+1] */
+/* counters of the last query call (host values; syncs the stream):
+ * [0] queries handled by the fused warp kernel, [1] by the CTA kernel,
+ * [2] by the global-memory kernel, [3] total locations gathered,
+ * [4] total features probed, [5] total table buckets (32 B) read             */
+int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8]);
+/* number of kernel launches issued by this library in this process           */
+uint64_t mcb200_kernel_launches (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

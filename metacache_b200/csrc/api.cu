@@ -1,0 +1,1009 @@
+// C ABI of libmcb200 (see include/mcb200.h): host-side resource management and
+// the stream choreography around the kernels.  No compute happens on the CPU.
+#include "internal.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace mcb {
+unsigned long long g_launches = 0;
+}
+using namespace mcb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string t_error;
+
+static int fail (int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    t_error = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(MCB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fail(MCB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return nullptr; } } while (0)
+
+extern "C" int mcb200_abi_version (void) { return MCB200_ABI_VERSION; }
+extern "C" const char* mcb200_last_error (void) { return t_error.c_str(); }
+extern "C" int mcb200_device_count (void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" uint32_t mcb200_max_supported_locations_per_feature (void) { return 254; }
+extern "C" uint64_t mcb200_kernel_launches (void) { return g_launches; }
+
+// grow-only device buffer
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure (size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release () { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <class T> struct PinBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure (size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(want, 1) * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release () { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+// ---------------------------------------------------------------------------
+// feature store
+// ---------------------------------------------------------------------------
+struct Part {
+    Bucket*   buckets = nullptr;
+    uint64_t  nbuckets = 0;
+    uint64_t* values = nullptr;
+    uint64_t  nkeys = 0, nvalues = 0;        // declared
+    uint64_t  keys_loaded = 0, values_loaded = 0;
+    bool      begun = false, finished = false;
+};
+
+struct mcb200_db {
+    int device = 0;
+    int sm_count = 148;
+    std::vector<Part> parts;
+    uint64_t* d_tax = nullptr;
+    uint32_t  n_tax = 0;
+    int*      d_error = nullptr;
+    cudaStream_t stream = nullptr;
+    // staging for host appends
+    DevBuf<uint32_t> st_keys; DevBuf<uint8_t> st_sizes; DevBuf<uint64_t> st_off;
+    void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+};
+
+static int use_device (int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MCB200_ENODEVICE, "no CUDA device available (libmcb200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(MCB200_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
+    if (n_parts == 0) { fail(MCB200_EINVAL, "n_parts must be >= 1"); return nullptr; }
+    if (use_device(device) != 0) return nullptr;
+    mcb200_db* db = new (std::nothrow) mcb200_db;
+    if (!db) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
+    db->device = device;
+    db->parts.resize(n_parts);
+    cudaDeviceProp prop;
+    CUP(cudaGetDeviceProperties(&prop, device));
+    db->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fail(MCB200_ENODEVICE, "device %d is sm_%d%d; libmcb200 is built for sm_100a only", device, prop.major, prop.minor);
+        delete db; return nullptr;
+    }
+    CUP(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    CUP(cudaMalloc(&db->d_error, sizeof(int)));
+    CUP(cudaMemset(db->d_error, 0, sizeof(int)));
+    return db;
+}
+
+static void free_part (Part& p) {
+    if (p.buckets) cudaFree(p.buckets);
+    if (p.values) cudaFree(p.values);
+    p = Part{};
+}
+
+extern "C" void mcb200_db_close (mcb200_db* db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    for (auto& p : db->parts) free_part(p);
+    if (db->d_tax) cudaFree(db->d_tax);
+    if (db->d_error) cudaFree(db->d_error);
+    db->st_keys.release(); db->st_sizes.release(); db->st_off.release();
+    if (db->scan_tmp) cudaFree(db->scan_tmp);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+#define CHECK_DB(db, part) \
+    if (!(db)) return fail(MCB200_EINVAL, "null database handle"); \
+    if ((part) >= (db)->parts.size()) return fail(MCB200_EINVAL, "part %u out of range (%zu parts)", unsigned(part), (db)->parts.size()); \
+    CU(cudaSetDevice((db)->device));
+
+extern "C" int mcb200_db_part_begin (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues,
+                                     float max_load_factor) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    free_part(p);
+    float lf = max_load_factor;
+    if (!(lf > 0.f)) lf = 0.5f;
+    if (lf > 0.95f) lf = 0.95f;
+    const double slots = double(nkeys) / lf;
+    p.nbuckets = std::max<uint64_t>(uint64_t(slots / 2.0) + 1, 16);
+    if (p.nbuckets >= (1ull << 32)) return fail(MCB200_EINVAL, "table too large (%llu buckets)", (unsigned long long)p.nbuckets);
+    p.nkeys = nkeys; p.nvalues = nvalues;
+    CU(cudaMalloc(&p.buckets, p.nbuckets * sizeof(Bucket)));
+    CU(cudaMemsetAsync(p.buckets, 0, p.nbuckets * sizeof(Bucket), db->stream));
+    CU(cudaMalloc(&p.values, (nvalues + 4) * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(db->d_error, 0, sizeof(int), db->stream));
+    p.begun = true;
+    return 0;
+}
+
+static int append_common (mcb200_db* db, Part& p, const uint32_t* d_keys, const uint8_t* d_sizes,
+                          uint64_t nkeys, uint64_t nvalues) {
+    // values for this batch are already at p.values + p.values_loaded
+    CU(db->st_off.ensure(nkeys + 1));
+    device_scan_sizes(d_sizes, nkeys, p.values_loaded, db->st_off.p, db->scan_tmp, db->scan_tmp_bytes, db->stream);
+    launch_table_insert(p.buckets, p.nbuckets, d_keys, d_sizes, db->st_off.p, p.values, nkeys,
+                        db->d_error, db->stream);
+    CU(cudaGetLastError());
+    p.keys_loaded += nkeys; p.values_loaded += nvalues;
+    return 0;
+}
+
+extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,
+                                      const uint8_t* sizes, const uint64_t* values,
+                                      uint64_t nkeys, uint64_t nvalues) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
+    if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
+        return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
+    if (nkeys == 0) return 0;
+    CU(db->st_keys.ensure(nkeys)); CU(db->st_sizes.ensure(nkeys));
+    CU(cudaMemcpyAsync(db->st_keys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, db->stream));
+    CU(cudaMemcpyAsync(db->st_sizes.p, sizes, nkeys, cudaMemcpyHostToDevice, db->stream));
+    CU(cudaMemcpyAsync(p.values + p.values_loaded, values, nvalues * 8, cudaMemcpyHostToDevice, db->stream));
+    int rc = append_common(db, p, db->st_keys.p, db->st_sizes.p, nkeys, nvalues);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(db->stream));     // host buffers may be reused by the caller
+    return 0;
+}
+
+extern "C" int mcb200_db_part_append_device (mcb200_db* db, uint32_t part, const uint32_t* d_keys,
+                                             const uint8_t* d_sizes, const uint64_t* d_values,
+                                             uint64_t nkeys, uint64_t nvalues) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
+    if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
+        return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
+    if (nkeys == 0) return 0;
+    CU(cudaMemcpyAsync(p.values + p.values_loaded, d_values, nvalues * 8, cudaMemcpyDeviceToDevice, db->stream));
+    int rc = append_common(db, p, d_keys, d_sizes, nkeys, nvalues);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.begun) return fail(MCB200_ESTATE, "part %u: finish without begin", part);
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, db->d_error, sizeof(int), cudaMemcpyDeviceToHost, db->stream));
+    CU(cudaStreamSynchronize(db->stream));
+    if (err == 1) return fail(MCB200_EINVAL, "part %u: hash table full", part);
+    if (err == 2) return fail(MCB200_EINVAL, "part %u: duplicate feature key in input", part);
+    if (p.keys_loaded != p.nkeys || p.values_loaded != p.nvalues)
+        return fail(MCB200_EINVAL, "part %u: loaded %llu/%llu keys, %llu/%llu values", part,
+                    (unsigned long long)p.keys_loaded, (unsigned long long)p.nkeys,
+                    (unsigned long long)p.values_loaded, (unsigned long long)p.nvalues);
+    p.finished = true;
+    return 0;
+}
+
+extern "C" int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const char* path,
+                                          float max_load_factor) {
+    CHECK_DB(db, part);
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(MCB200_EIO, "cannot open '%s'", path);
+    uint64_t hdr[3];
+    if (fread(hdr, 8, 3, f) != 3) { fclose(f); return fail(MCB200_EIO, "'%s': truncated header", path); }
+    const uint64_t nkeys = hdr[0], nvalues = hdr[1], batch = hdr[2] ? hdr[2] : (1u << 20);
+    int rc = mcb200_db_part_begin(db, part, nkeys, nvalues, max_load_factor);
+    if (rc) { fclose(f); return rc; }
+    std::vector<uint32_t> keys; std::vector<uint8_t> sizes; std::vector<uint64_t> vals;
+    for (uint64_t done = 0; done < nkeys; ) {
+        const uint64_t b = std::min<uint64_t>(batch, nkeys - done);
+        keys.resize(b); sizes.resize(b);
+        if (fread(keys.data(), 4, b, f) != b || fread(sizes.data(), 1, b, f) != b) {
+            fclose(f); return fail(MCB200_EIO, "'%s': truncated batch", path);
+        }
+        uint64_t nv = 0;
+        for (uint64_t i = 0; i < b; ++i) nv += sizes[i];
+        vals.resize(nv);
+        if (nv && fread(vals.data(), 8, nv, f) != nv) { fclose(f); return fail(MCB200_EIO, "'%s': truncated values", path); }
+        rc = mcb200_db_part_append(db, part, keys.data(), sizes.data(), vals.data(), b, nv);
+        if (rc) { fclose(f); return rc; }
+        done += b;
+    }
+    fclose(f);
+    return mcb200_db_part_finish(db, part);
+}
+
+extern "C" int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax, uint32_t n) {
+    if (!db) return fail(MCB200_EINVAL, "null database handle");
+    CU(cudaSetDevice(db->device));
+    if (db->d_tax) { cudaFree(db->d_tax); db->d_tax = nullptr; db->n_tax = 0; }
+    if (!tax || !n) return 0;
+    CU(cudaMalloc(&db->d_tax, uint64_t(n) * 8));
+    CU(cudaMemcpy(db->d_tax, tax, uint64_t(n) * 8, cudaMemcpyHostToDevice));
+    db->n_tax = n;
+    return 0;
+}
+
+extern "C" uint32_t mcb200_db_part_count (const mcb200_db* db) { return db ? uint32_t(db->parts.size()) : 0; }
+extern "C" uint64_t mcb200_db_key_count (const mcb200_db* db, uint32_t part) {
+    return (db && part < db->parts.size()) ? db->parts[part].keys_loaded : 0; }
+extern "C" uint64_t mcb200_db_value_count (const mcb200_db* db, uint32_t part) {
+    return (db && part < db->parts.size()) ? db->parts[part].values_loaded : 0; }
+extern "C" uint64_t mcb200_db_bucket_count (const mcb200_db* db, uint32_t part) {
+    return (db && part < db->parts.size()) ? db->parts[part].nbuckets * 2 : 0; }
+extern "C" uint64_t mcb200_db_device_bytes (const mcb200_db* db, uint32_t part) {
+    if (!db || part >= db->parts.size()) return 0;
+    const Part& p = db->parts[part];
+    return p.nbuckets * sizeof(Bucket) + (p.nvalues + 4) * 8;
+}
+extern "C" int mcb200_db_device (const mcb200_db* db) { return db ? db->device : -1; }
+
+extern "C" int mcb200_db_part_export (const mcb200_db* db, uint32_t part, uint32_t* keys,
+                                      uint8_t* sizes, uint64_t* values) {
+    CHECK_DB(db, part);
+    const Part& p = db->parts[part];
+    if (!p.finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (table_export(p.buckets, p.nbuckets, p.values, p.keys_loaded, p.values_loaded, keys, sizes,
+                     values, db->stream) != 0)
+        return fail(MCB200_ECUDA, "export failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// workspace (device-resident pipeline)
+// ---------------------------------------------------------------------------
+struct mcb200_workspace {
+    mcb200_db* db = nullptr;
+    uint32_t max_queries = 0, max_seqs = 0, maxc = 2;
+    uint64_t max_bases = 0;
+    bool want_allhits = false;
+    uint32_t warp_cap = 512;
+
+    DevBuf<uint32_t> codes, amb, seq_nwin, seq_win_off, win_seq, qry_win_off, feats;
+    DevBuf<uint32_t> heavy_list, heavy_count;
+    DevBuf<unsigned long long> counters, scratch_cursor;
+    DevBuf<uint64_t> scratch;            // 12 B per entry: keys then cnt
+    uint64_t scratch_entries = 0;
+    DevBuf<int> error;
+    DevBuf<mcb200_candidate> part_tops;
+    DevBuf<uint64_t> hit_counts, hit_offsets, allhits;
+    void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+
+    // state of the last sketch call
+    mcb200_dev_queries q{};
+    SketchParams sk{16, 16, 127, 112};
+    uint64_t win_bound = 0;
+    bool sketched = false;
+    cudaStream_t last_stream = nullptr;
+};
+
+static int validate_sketching (const mcb200_sketching* sk) {
+    if (!sk) return fail(MCB200_EINVAL, "null sketching options");
+    if (sk->kmerlen < 1 || sk->kmerlen > 16) return fail(MCB200_EINVAL, "kmerlen %u unsupported (1..16)", sk->kmerlen);
+    if (sk->sketchlen < 1 || sk->sketchlen > 32) return fail(MCB200_EINVAL, "sketchlen %u unsupported (1..32)", sk->sketchlen);
+    if (sk->winlen < sk->kmerlen || sk->winlen > 4096) return fail(MCB200_EINVAL, "winlen %u unsupported (kmerlen..4096)", sk->winlen);
+    if (sk->winstride < 1) return fail(MCB200_EINVAL, "winstride must be >= 1");
+    return 0;
+}
+
+extern "C" mcb200_workspace* mcb200_workspace_create (mcb200_db* db, uint32_t max_queries,
+                                                      uint32_t max_seqs, uint64_t max_bases,
+                                                      uint32_t max_candidates, int want_all_hits) {
+    if (!db) { fail(MCB200_EINVAL, "null database handle"); return nullptr; }
+    if (max_candidates < 1 || max_candidates > 32) { fail(MCB200_EINVAL, "max_candidates %u unsupported (1..32)", max_candidates); return nullptr; }
+    if (max_bases >= (1ull << 32) - 4096) { fail(MCB200_EINVAL, "max_bases must be < 4 Gi per workspace"); return nullptr; }
+    if (max_seqs < max_queries) max_seqs = max_queries;
+    CUP(cudaSetDevice(db->device));
+    mcb200_workspace* ws = new (std::nothrow) mcb200_workspace;
+    if (!ws) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
+    ws->db = db; ws->max_queries = max_queries; ws->max_seqs = max_seqs; ws->max_bases = max_bases;
+    ws->maxc = max_candidates; ws->want_allhits = want_all_hits != 0;
+    const uint64_t padded = ((max_bases + 31) / 32) * 32 + 512;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&] (cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(ws->codes.ensure(padded / 16 + 64)); ok(ws->amb.ensure(padded / 32 + 64));
+    ok(ws->seq_nwin.ensure(max_seqs + 1)); ok(ws->seq_win_off.ensure(max_seqs + 2));
+    ok(ws->qry_win_off.ensure(max_queries + 1));
+    ok(ws->heavy_list.ensure(max_queries)); ok(ws->heavy_count.ensure(2));
+    ok(ws->counters.ensure(64 * 8)); ok(ws->scratch_cursor.ensure(1)); ok(ws->error.ensure(1));
+    if (e == cudaSuccess) e = cudaMemset(ws->codes.p, 0, ws->codes.n * 4);
+    if (e == cudaSuccess) e = cudaMemset(ws->amb.p, 0xFF, ws->amb.n * 4);
+    if (e == cudaSuccess) e = cudaMemset(ws->error.p, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ws->counters.p, 0, 64 * 8 * 8);
+    if (e != cudaSuccess) {
+        fail(MCB200_ECUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
+        delete ws; return nullptr;
+    }
+    return ws;
+}
+
+extern "C" void mcb200_workspace_destroy (mcb200_workspace* ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->db->device);
+    ws->codes.release(); ws->amb.release(); ws->seq_nwin.release(); ws->seq_win_off.release();
+    ws->win_seq.release(); ws->qry_win_off.release(); ws->feats.release(); ws->heavy_list.release();
+    ws->heavy_count.release(); ws->counters.release(); ws->scratch_cursor.release();
+    ws->scratch.release(); ws->error.release(); ws->part_tops.release(); ws->hit_counts.release();
+    ws->hit_offsets.release(); ws->allhits.release();
+    if (ws->scan_tmp) cudaFree(ws->scan_tmp);
+    delete ws;
+}
+
+extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                     const mcb200_sketching* sk, void* stream) {
+    if (!ws || !q) return fail(MCB200_EINVAL, "null argument");
+    int rc = validate_sketching(sk);
+    if (rc) return rc;
+    if (q->n_queries > ws->max_queries || q->n_seqs > ws->max_seqs || q->n_bases > ws->max_bases)
+        return fail(MCB200_EINVAL, "batch exceeds workspace capacity (%u/%u queries, %u/%u seqs, %llu/%llu bases)",
+                    q->n_queries, ws->max_queries, q->n_seqs, ws->max_seqs,
+                    (unsigned long long)q->n_bases, (unsigned long long)ws->max_bases);
+    if (q->n_seqs < q->n_queries) return fail(MCB200_EINVAL, "every query needs at least one sequence");
+    if (reinterpret_cast<uintptr_t>(q->bases) & 15) return fail(MCB200_EINVAL, "bases must be 16-byte aligned");
+    CU(cudaSetDevice(ws->db->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->q = *q; ws->sk = SketchParams{sk->kmerlen, sk->sketchlen, sk->winlen, sk->winstride};
+    ws->last_stream = st;
+    ws->sketched = false;
+    if (q->n_queries == 0) { ws->sketched = true; ws->win_bound = 0; return 0; }
+
+    // upper bound of the window count: every sequence has <= len/stride + 2 windows
+    const uint64_t bound = q->n_bases / sk->winstride + 2ull * q->n_seqs;
+    if (bound * sk->sketchlen >= (1ull << 32)) return fail(MCB200_EINVAL, "too many windows for one call; split the batch");
+    ws->win_bound = bound;
+    CU(ws->win_seq.ensure(bound));
+    CU(ws->feats.ensure(bound * sk->sketchlen));
+
+    launch_encode(q->bases, q->n_bases, ws->codes.p, ws->amb.p, st);
+    launch_count_windows(q->seq_offsets, q->n_seqs, ws->sk, ws->seq_nwin.p, st);
+    CU(cudaMemsetAsync(ws->seq_nwin.p + q->n_seqs, 0, 4, st));
+    device_scan_u32(ws->seq_nwin.p, ws->seq_win_off.p, uint64_t(q->n_seqs) + 1, ws->scan_tmp, ws->scan_tmp_bytes, st);
+    launch_fill_windows(ws->seq_win_off.p, q->seq_query, q->n_seqs, q->n_queries, ws->win_seq.p,
+                        ws->qry_win_off.p, st);
+    launch_sketch(ws->codes.p, ws->amb.p, q->seq_offsets, ws->seq_win_off.p, ws->win_seq.p,
+                  ws->seq_win_off.p + q->n_seqs, ws->sk, ws->feats.p, ws->db->sm_count, st);
+    CU(cudaGetLastError());
+    ws->sketched = true;
+    return 0;
+}
+
+static int ensure_scratch (mcb200_workspace* ws, uint64_t entries) {
+    if (entries <= ws->scratch_entries) return 0;
+    ws->scratch.release();
+    // 12 bytes per entry stored as u64 words: 1.5 words per entry
+    CU(ws->scratch.ensure(entries + entries / 2 + 2));
+    ws->scratch_entries = entries;
+    return 0;
+}
+
+static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top) {
+    const Part& p = ws->db->parts[part];
+    QueryArgs a{};
+    a.feats = ws->feats.p; a.qry_win_off = ws->qry_win_off.p; a.max_win = ws->q.max_win;
+    a.tax_of_tgt = ws->db->d_tax; a.n_tax = ws->db->n_tax;
+    a.nq = ws->q.n_queries; a.s = ws->sk.s; a.maxc = ws->maxc;
+    a.table = TableView{p.buckets, p.nbuckets, p.values};
+    a.top = d_top;
+    a.allhits = nullptr; a.allhits_off = nullptr;
+    a.heavy_list = ws->heavy_list.p; a.heavy_count = ws->heavy_count.p;
+    a.scratch = ws->scratch.p; a.scratch_entries = ws->scratch_entries;
+    a.scratch_cursor = ws->scratch_cursor.p;
+    a.counters = ws->counters.p; a.error = ws->error.p;
+    return a;
+}
+
+static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
+                       const uint64_t* allhits_off, cudaStream_t st) {
+    if (ws->scratch_entries == 0) { int rc = ensure_scratch(ws, 1ull << 22); if (rc) return rc; }
+    QueryArgs a = make_args(ws, part, d_top);
+    if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 8, st));
+    CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
+    launch_query_warp(a, ws->warp_cap, ws->db->sm_count, st);
+    launch_query_heavy(a, ws->db->sm_count, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
+                                         void* stream) {
+    if (!ws || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (!ws->sketched) return fail(MCB200_ESTATE, "mcb200_sketch_device must run first");
+    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished)
+        return fail(MCB200_ESTATE, "part %u not loaded", part);
+    CU(cudaSetDevice(ws->db->device));
+    if (ws->q.n_queries == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    // a read that outgrows the scratch pool raises the sticky device flag 3; callers see it
+    // through mcb200_workspace_counters() (device API) or batch_wait (which grows and retries)
+    return query_part(ws, part, d_top, nullptr, st);
+}
+
+extern "C" int mcb200_merge_candidates_device (mcb200_workspace* ws, const mcb200_candidate* d_parts,
+                                               uint32_t n_lists, uint32_t n_queries,
+                                               mcb200_candidate* d_out, void* stream) {
+    if (!ws || !d_parts || !d_out) return fail(MCB200_EINVAL, "null argument");
+    CU(cudaSetDevice(ws->db->device));
+    launch_merge_candidates(d_parts, n_lists, n_queries, ws->maxc, ws->db->d_tax, ws->db->n_tax, d_out,
+                            static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// layout of all-hits: the reference concatenates parts per query
+// (host_hashmap.hpp:706-719).  We produce [query][part] segments: offsets index
+// = q * np + p.  Counting kernel writes counts[p * nq + q]; transpose kernel
+// builds the interleaved count vector that is scanned.
+__global__ void interleave_counts_kernel (const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                          uint32_t nq, uint32_t np) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= uint64_t(nq) * np) return;
+    const uint32_t q = uint32_t(i / np), p = uint32_t(i % np);
+    out[i] = in[uint64_t(p) * nq + q];
+}
+__global__ void part_offsets_kernel (const uint64_t* __restrict__ offs, uint64_t* __restrict__ out,
+                                     uint32_t nq, uint32_t np, uint32_t p) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) out[q] = offs[uint64_t(q) * np + p];
+}
+
+extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                    const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream) {
+    if (!ws || !q || !d_top) return fail(MCB200_EINVAL, "null argument");
+    for (auto& p : ws->db->parts) if (!p.finished) return fail(MCB200_ESTATE, "database part not loaded");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = mcb200_sketch_device(ws, q, sk, stream);
+    if (rc) return rc;
+    const uint32_t np = uint32_t(ws->db->parts.size());
+    const uint32_t nq = q->n_queries;
+    if (nq == 0) return 0;
+
+    if (ws->want_allhits) {
+        CU(ws->hit_counts.ensure(uint64_t(nq) * np * 2 + 2));
+        CU(ws->hit_offsets.ensure(uint64_t(nq) * np + 1 + nq));
+        uint64_t* cnt_pm = ws->hit_counts.p;                       // [p][q]
+        uint64_t* cnt_il = ws->hit_counts.p + uint64_t(nq) * np;   // [q][p] + 1
+        for (uint32_t p = 0; p < np; ++p) {
+            QueryArgs a = make_args(ws, p, nullptr);
+            launch_count_hits(a, cnt_pm + uint64_t(p) * nq, st);
+        }
+        const uint64_t tot = uint64_t(nq) * np;
+        interleave_counts_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cnt_pm, cnt_il, nq, np);
+        count_launch();
+        CU(cudaMemsetAsync(cnt_il + tot, 0, 8, st));
+        device_scan_u64(cnt_il, ws->hit_offsets.p, tot + 1, ws->scan_tmp, ws->scan_tmp_bytes, st);
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, ws->hit_offsets.p + tot, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(ws->allhits.ensure(total + 1));
+    }
+
+    mcb200_candidate* dst = d_top;
+    if (np > 1) { CU(ws->part_tops.ensure(uint64_t(np) * nq * ws->maxc)); }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        for (uint32_t p = 0; p < np; ++p) {
+            if (np > 1) dst = ws->part_tops.p + uint64_t(p) * nq * ws->maxc;
+            const uint64_t* poff = nullptr;
+            if (ws->want_allhits) {
+                uint64_t* v = ws->hit_offsets.p + uint64_t(nq) * np + 1;
+                part_offsets_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ws->hit_offsets.p, v, nq, np, p);
+                count_launch();
+                poff = v;
+            }
+            rc = query_part(ws, p, dst, poff, st);
+            if (rc) return rc;
+        }
+        if (np > 1) {
+            launch_merge_candidates(ws->part_tops.p, np, nq, ws->maxc, ws->db->d_tax, ws->db->n_tax, d_top, st);
+            CU(cudaGetLastError());
+        }
+        // The scratch-pool check needs a sync; callers on the fast path check it
+        // later through mcb200_workspace_counters()/batch_wait (sticky flag).
+        if (!ws->want_allhits) return 0;
+        int err = 0;
+        CU(cudaMemcpyAsync(&err, ws->error.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (err != 3) return 0;
+        CU(cudaMemsetAsync(ws->error.p, 0, sizeof(int), st));
+        rc = ensure_scratch(ws, ws->scratch_entries * 8);
+        if (rc) return rc;
+    }
+    return fail(MCB200_ENOMEM, "scratch pool exhausted");
+}
+
+extern "C" uint32_t mcb200_workspace_num_windows (const mcb200_workspace* ws) {
+    if (!ws || !ws->sketched || ws->q.n_queries == 0) return 0;
+    cudaSetDevice(ws->db->device);
+    uint32_t n = 0;
+    cudaMemcpyAsync(&n, ws->seq_win_off.p + ws->q.n_seqs, 4, cudaMemcpyDeviceToHost, ws->last_stream);
+    cudaStreamSynchronize(ws->last_stream);
+    return n;
+}
+extern "C" const uint32_t* mcb200_workspace_sketches (const mcb200_workspace* ws) { return ws ? ws->feats.p : nullptr; }
+extern "C" const uint32_t* mcb200_workspace_query_windows (const mcb200_workspace* ws) { return ws ? ws->qry_win_off.p : nullptr; }
+extern "C" const uint64_t* mcb200_workspace_allhits (const mcb200_workspace* ws) { return ws ? ws->allhits.p : nullptr; }
+extern "C" const uint64_t* mcb200_workspace_allhits_offsets (const mcb200_workspace* ws) { return ws ? ws->hit_offsets.p : nullptr; }
+
+extern "C" int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8]) {
+    if (!ws || !out) return fail(MCB200_EINVAL, "null argument");
+    CU(cudaSetDevice(ws->db->device));
+    unsigned long long h[64 * 8];
+    int err = 0;
+    CU(cudaMemcpyAsync(h, ws->counters.p, sizeof h, cudaMemcpyDeviceToHost, ws->last_stream));
+    CU(cudaMemcpyAsync(&err, ws->error.p, sizeof(int), cudaMemcpyDeviceToHost, ws->last_stream));
+    CU(cudaMemsetAsync(ws->counters.p, 0, sizeof h, ws->last_stream));
+    CU(cudaStreamSynchronize(ws->last_stream));
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int s = 0; s < 64; ++s) for (int i = 0; i < 8; ++i) out[i] += h[s * 8 + i];
+    if (err == 3) return fail(MCB200_ENOMEM, "scratch pool exhausted by a huge read; results of that read are empty");
+    if (err) return fail(MCB200_ECUDA, "device error flag %d", err);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// part builder (sketch targets on the device)
+// ---------------------------------------------------------------------------
+__global__ void offsets64_to_32_kernel (const uint64_t* in, uint32_t* out, uint64_t base, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = uint32_t(in[i] - base);
+}
+__global__ void iota_kernel (uint32_t* out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+__global__ void consumed_windows_kernel (const uint32_t* seq_off, uint32_t n, SketchParams p, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // add_target counts consumed sketches = windows with >= k characters (host_hashmap.hpp:576-590)
+    const uint32_t len = seq_off[i + 1] - seq_off[i];
+    uint32_t c = 0;
+    if (len <= p.w) c = (len >= p.k) ? 1u : 0u;
+    else {
+        const uint32_t full = (len - p.w) / p.stride + 1;
+        c = full;
+        const uint64_t first = uint64_t(full) * p.stride;
+        if (first < len && len - first >= p.k) ++c;
+    }
+    out[i] = c;
+}
+
+extern "C" int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
+                                                  const char* d_bases, const uint64_t* d_seq_offsets,
+                                                  uint32_t n_targets, uint32_t first_target_id,
+                                                  const mcb200_sketching* sk, uint32_t max_locations,
+                                                  float max_load_factor, uint32_t* out_windows) {
+    CHECK_DB(db, part);
+    int rc = validate_sketching(sk);
+    if (rc) return rc;
+    if (max_locations < 1 || max_locations > 254) return fail(MCB200_EINVAL, "max_locations %u unsupported (1..254)", max_locations);
+    if (n_targets == 0) return fail(MCB200_EINVAL, "no targets");
+    cudaStream_t st = db->stream;
+    std::vector<uint64_t> h_off(uint64_t(n_targets) + 1);
+    CU(cudaMemcpy(h_off.data(), d_seq_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost));
+
+    // sketch targets in chunks of < 2 Gi bases / < 2^31 features, collect (key,size,values) per chunk
+    // then a final merge: chunks are in target order, so a stable sort over the concatenation of
+    // the per-chunk pair lists keeps (tgt,win) order.  To keep memory bounded we instead sketch all
+    // chunks into ONE feature array and sort once.
+    const SketchParams sp{sk->kmerlen, sk->sketchlen, sk->winlen, sk->winstride};
+    uint64_t total_windows = 0;
+    for (uint32_t i = 0; i < n_targets; ++i)
+        total_windows += [&] { const uint64_t len = h_off[i + 1] - h_off[i];
+                               if (len <= sp.w) return uint64_t(1);
+                               const uint64_t full = (len - sp.w) / sp.stride + 1;
+                               return full + ((full * sp.stride < len) ? 1 : 0); }();
+    if (total_windows * sp.s >= (1ull << 31)) return fail(MCB200_EINVAL, "part too large for one build (%llu windows)", (unsigned long long)total_windows);
+
+    DevBuf<uint32_t> feats, win_seq, seq_win_off, seq_off32, seq_query, dummy_maxwin;
+    CU(feats.ensure(total_windows * sp.s)); CU(win_seq.ensure(total_windows));
+    CU(seq_win_off.ensure(uint64_t(n_targets) + 1));
+    std::vector<uint32_t> h_seq_win_off(uint64_t(n_targets) + 1, 0);
+
+    const uint64_t kChunkBases = 1ull << 30;
+    uint32_t t0 = 0; uint64_t win_done = 0;
+    while (t0 < n_targets) {
+        uint32_t t1 = t0;
+        while (t1 < n_targets && (t1 == t0 || h_off[t1 + 1] - h_off[t0] <= kChunkBases)) ++t1;
+        const uint64_t nb = h_off[t1] - h_off[t0];
+        if (nb >= (1ull << 32) - 8192) return fail(MCB200_EINVAL, "target %u too long for the device builder", t0);
+        const uint32_t ns = t1 - t0;
+        if ((h_off[t0] & 15) != 0) {
+            // bulk/vector loads need 16-byte alignment: copy the chunk to an aligned buffer
+        }
+        mcb200_workspace* ws = mcb200_workspace_create(db, ns, ns, nb + 16, 1, 0);
+        if (!ws) return MCB200_ECUDA;
+        DevBuf<char> aligned;
+        const char* bases = d_bases + h_off[t0];
+        if (reinterpret_cast<uintptr_t>(bases) & 15) {
+            cudaError_t e = aligned.ensure(nb + 64);
+            if (e != cudaSuccess) { mcb200_workspace_destroy(ws); return fail(MCB200_ECUDA, "alloc failed"); }
+            cudaMemcpyAsync(aligned.p, bases, nb, cudaMemcpyDeviceToDevice, st);
+            bases = aligned.p;
+        }
+        seq_off32.ensure(ns + 1); seq_query.ensure(ns); dummy_maxwin.ensure(ns);
+        offsets64_to_32_kernel<<<(ns + 1 + 255) / 256, 256, 0, st>>>(d_seq_offsets + t0, seq_off32.p, h_off[t0], ns + 1);
+        iota_kernel<<<(ns + 255) / 256, 256, 0, st>>>(seq_query.p, ns);
+        count_launch(2);
+        mcb200_dev_queries q{bases, seq_off32.p, seq_query.p, dummy_maxwin.p, ns, ns, nb};
+        rc = mcb200_sketch_device(ws, &q, sk, st);
+        if (rc) { mcb200_workspace_destroy(ws); aligned.release(); return rc; }
+        const uint32_t nw = mcb200_workspace_num_windows(ws);
+        std::vector<uint32_t> hw(ns + 1);
+        cudaMemcpyAsync(hw.data(), ws->seq_win_off.p, (ns + 1) * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(feats.p + win_done * sp.s, ws->feats.p, uint64_t(nw) * sp.s * 4, cudaMemcpyDeviceToDevice, st);
+        if (out_windows) {
+            consumed_windows_kernel<<<(ns + 255) / 256, 256, 0, st>>>(seq_off32.p, ns, sp, ws->seq_nwin.p);
+            count_launch();
+            cudaMemcpyAsync(out_windows + t0, ws->seq_nwin.p, ns * 4, cudaMemcpyDeviceToHost, st);
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        mcb200_workspace_destroy(ws); aligned.release();
+        if (e != cudaSuccess) return fail(MCB200_ECUDA, "target sketching failed: %s", cudaGetErrorString(e));
+        for (uint32_t i = 0; i <= ns; ++i) h_seq_win_off[t0 + i] = uint32_t(win_done + hw[i]);
+        win_done += nw;
+        t0 = t1;
+    }
+    seq_off32.release(); seq_query.release(); dummy_maxwin.release();
+    if (win_done != total_windows) return fail(MCB200_ECUDA, "window count mismatch (%llu vs %llu)", (unsigned long long)win_done, (unsigned long long)total_windows);
+    CU(cudaMemcpyAsync(seq_win_off.p, h_seq_win_off.data(), h_seq_win_off.size() * 4, cudaMemcpyHostToDevice, st));
+    {   // win_seq for the whole part
+        DevBuf<uint32_t> sq, qwo; CU(sq.ensure(n_targets)); CU(qwo.ensure(uint64_t(n_targets) + 1));
+        iota_kernel<<<(n_targets + 255) / 256, 256, 0, st>>>(sq.p, n_targets);
+        count_launch();
+        launch_fill_windows(seq_win_off.p, sq.p, n_targets, n_targets, win_seq.p, qwo.p, st);
+        CU(cudaStreamSynchronize(st));
+        sq.release(); qwo.release();
+    }
+    BuiltPart bp{};
+    rc = build_from_sketches(feats.p, win_seq.p, seq_win_off.p, total_windows, sp.s, first_target_id,
+                             max_locations, bp, st);
+    feats.release(); win_seq.release(); seq_win_off.release();
+    if (rc) return fail(MCB200_ECUDA, "device part build failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    rc = mcb200_db_part_begin(db, part, bp.nkeys, bp.nvalues, max_load_factor);
+    if (!rc) rc = mcb200_db_part_append_device(db, part, bp.keys, bp.sizes, bp.values, bp.nkeys, bp.nvalues);
+    if (bp.keys) cudaFree(bp.keys);
+    if (bp.sizes) cudaFree(bp.sizes);
+    if (bp.values) cudaFree(bp.values);
+    if (rc) return rc;
+    return mcb200_db_part_finish(db, part);
+}
+
+// ---------------------------------------------------------------------------
+// query batch (host buffers)
+// ---------------------------------------------------------------------------
+struct Slot_ {
+    PinBuf<char> h_bases; PinBuf<uint32_t> h_seq_off, h_seq_query, h_max_win;
+    DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off, d_seq_query, d_max_win;
+    DevBuf<mcb200_candidate> d_top; PinBuf<mcb200_candidate> h_top;
+    PinBuf<uint32_t> h_feats, h_qry_win_off; PinBuf<uint64_t> h_allhits, h_allhits_off;
+    uint32_t n_queries = 0, n_seqs = 0, n_windows = 0; uint64_t n_bases = 0;
+    uint32_t sub_queries = 0, sub_s = 0;
+    bool submitted = false, waited = false, sketches_fetched = false, allhits_fetched = false;
+    mcb200_workspace* ws = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    float total_ms = 0, kernels_ms = 0;
+};
+
+struct mcb200_batch {
+    mcb200_db* db = nullptr;
+    uint32_t max_queries = 0, maxc = 2; uint64_t max_bases = 0; bool allhits = false;
+    std::vector<Slot_> slots;
+};
+
+extern "C" mcb200_batch* mcb200_batch_create (mcb200_db* db, uint32_t max_queries, uint64_t max_bases,
+                                              uint32_t max_candidates, int copy_all_hits, uint32_t n_slots) {
+    if (!db || max_queries == 0 || n_slots == 0) { fail(MCB200_EINVAL, "bad batch parameters"); return nullptr; }
+    if (max_candidates < 1 || max_candidates > 32) { fail(MCB200_EINVAL, "max_candidates %u unsupported (1..32)", max_candidates); return nullptr; }
+    CUP(cudaSetDevice(db->device));
+    mcb200_batch* b = new (std::nothrow) mcb200_batch;
+    if (!b) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
+    b->db = db; b->max_queries = max_queries; b->maxc = max_candidates; b->max_bases = max_bases;
+    b->allhits = copy_all_hits != 0;
+    b->slots.resize(n_slots);
+    const uint32_t max_seqs = (max_queries > (1u << 30)) ? max_queries : max_queries * 2;
+    for (auto& s : b->slots) {
+        cudaError_t e = cudaSuccess;
+        auto ok = [&] (cudaError_t x) { if (e == cudaSuccess) e = x; };
+        ok(s.h_bases.ensure(max_bases + 64)); ok(s.h_seq_off.ensure(max_seqs + 1));
+        ok(s.h_seq_query.ensure(max_seqs)); ok(s.h_max_win.ensure(max_queries));
+        ok(s.d_bases.ensure(max_bases + 64)); ok(s.d_seq_off.ensure(max_seqs + 1));
+        ok(s.d_seq_query.ensure(max_seqs)); ok(s.d_max_win.ensure(max_queries));
+        ok(s.d_top.ensure(uint64_t(max_queries) * max_candidates));
+        ok(s.h_top.ensure(uint64_t(max_queries) * max_candidates));
+        ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        ok(cudaEventCreate(&s.ev_start)); ok(cudaEventCreate(&s.ev_k0));
+        ok(cudaEventCreate(&s.ev_k1)); ok(cudaEventCreate(&s.ev_done));
+        if (e != cudaSuccess) {
+            fail(MCB200_ECUDA, "batch allocation failed: %s", cudaGetErrorString(e));
+            mcb200_batch_destroy(b); return nullptr;
+        }
+        s.ws = mcb200_workspace_create(db, max_queries, max_seqs, max_bases, max_candidates, copy_all_hits);
+        if (!s.ws) { mcb200_batch_destroy(b); return nullptr; }
+        s.h_seq_off.p[0] = 0;
+    }
+    return b;
+}
+
+extern "C" void mcb200_batch_destroy (mcb200_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->db->device);
+    for (auto& s : b->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.h_bases.release(); s.h_seq_off.release(); s.h_seq_query.release(); s.h_max_win.release();
+        s.d_bases.release(); s.d_seq_off.release(); s.d_seq_query.release(); s.d_max_win.release();
+        s.d_top.release(); s.h_top.release(); s.h_feats.release(); s.h_qry_win_off.release();
+        s.h_allhits.release(); s.h_allhits_off.release();
+        if (s.ws) mcb200_workspace_destroy(s.ws);
+        if (s.ev_start) cudaEventDestroy(s.ev_start);
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete b;
+}
+
+#define CHECK_SLOT(b, slot) \
+    if (!(b)) return fail(MCB200_EINVAL, "null batch handle"); \
+    if ((slot) >= (b)->slots.size()) return fail(MCB200_EINVAL, "slot %u out of range", unsigned(slot));
+
+static inline bool slot_add (mcb200_batch* b, Slot_& s, const char* s1, uint64_t l1, const char* s2,
+                             uint64_t l2, uint32_t max_win) {
+    const uint32_t max_seqs = uint32_t(s.h_seq_query.n);
+    const uint32_t nseq = (l2 > 0) ? 2u : 1u;
+    if (s.n_queries + 1 > b->max_queries || s.n_seqs + nseq > max_seqs ||
+        s.n_bases + l1 + l2 > b->max_bases) return false;
+    memcpy(s.h_bases.p + s.n_bases, s1, l1);
+    s.n_bases += l1;
+    s.h_seq_query.p[s.n_seqs] = s.n_queries;
+    s.h_seq_off.p[++s.n_seqs] = uint32_t(s.n_bases);
+    if (l2 > 0) {
+        memcpy(s.h_bases.p + s.n_bases, s2, l2);
+        s.n_bases += l2;
+        s.h_seq_query.p[s.n_seqs] = s.n_queries;
+        s.h_seq_off.p[++s.n_seqs] = uint32_t(s.n_bases);
+    }
+    s.h_max_win.p[s.n_queries++] = max_win;
+    return true;
+}
+
+extern "C" int mcb200_batch_add_read (mcb200_batch* b, uint32_t slot, const char* seq1, uint64_t len1,
+                                      const char* seq2, uint64_t len2, uint32_t max_windows_in_range) {
+    CHECK_SLOT(b, slot);
+    Slot_& s = b->slots[slot];
+    if (s.submitted) return fail(MCB200_ESTATE, "slot %u: clear() before adding reads again", slot);
+    if ((len1 && !seq1) || (len2 && !seq2)) return fail(MCB200_EINVAL, "null sequence");
+    if (len1 + len2 > b->max_bases) return fail(MCB200_EINVAL, "read (%llu bases) larger than the whole batch", (unsigned long long)(len1 + len2));
+    // a read with an empty first mate keeps its (non-empty) second mate as only sequence
+    if (len1 == 0 && len2 > 0) return slot_add(b, s, seq2, len2, nullptr, 0, max_windows_in_range) ? 1 : 0;
+    return slot_add(b, s, seq1, len1, seq2, len2, max_windows_in_range) ? 1 : 0;
+}
+
+extern "C" int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const char* bases,
+                                           const uint64_t* offsets, uint32_t n_queries, int paired,
+                                           uint64_t insert_size_max, uint32_t winstride) {
+    CHECK_SLOT(b, slot);
+    Slot_& s = b->slots[slot];
+    if (s.submitted) return fail(MCB200_ESTATE, "slot %u: clear() before adding reads again", slot);
+    if (!bases || !offsets || winstride == 0) return fail(MCB200_EINVAL, "bad argument");
+    int64_t added = 0;
+    for (uint32_t i = 0; i < n_queries; ++i) {
+        const uint64_t o0 = offsets[paired ? 2 * uint64_t(i) : i];
+        const uint64_t o1 = offsets[(paired ? 2 * uint64_t(i) : i) + 1];
+        const uint64_t o2 = paired ? offsets[2 * uint64_t(i) + 2] : o1;
+        const uint64_t l1 = o1 - o0, l2 = o2 - o1;
+        // make_candidate_generation_rules (candidate_structs.hpp:134-151)
+        const uint32_t mw = uint32_t(2 + std::max<uint64_t>(l1 + l2, insert_size_max) / winstride);
+        bool ok;
+        if (l1 == 0 && l2 > 0) ok = slot_add(b, s, bases + o1, l2, nullptr, 0, mw);
+        else ok = slot_add(b, s, bases + o0, l1, bases + o1, l2, mw);
+        if (!ok) break;
+        ++added;
+    }
+    return added;
+}
+
+extern "C" int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200_sketching* sk) {
+    CHECK_SLOT(b, slot);
+    Slot_& s = b->slots[slot];
+    int rc = validate_sketching(sk);
+    if (rc) return rc;
+    CU(cudaSetDevice(b->db->device));
+    cudaStream_t st = s.stream;
+    s.submitted = true; s.waited = false; s.sketches_fetched = false; s.allhits_fetched = false;
+    s.sub_queries = s.n_queries; s.sub_s = sk->sketchlen;
+    CU(cudaEventRecord(s.ev_start, st));
+    if (s.n_queries == 0) { CU(cudaEventRecord(s.ev_k0, st)); CU(cudaEventRecord(s.ev_k1, st)); CU(cudaEventRecord(s.ev_done, st)); return 0; }
+    const uint64_t nb_pad = (s.n_bases + 15) & ~15ull;
+    memset(s.h_bases.p + s.n_bases, 0, nb_pad - s.n_bases);
+    CU(cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, nb_pad, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.d_seq_off.p, s.h_seq_off.p, (uint64_t(s.n_seqs) + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.d_seq_query.p, s.h_seq_query.p, uint64_t(s.n_seqs) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.d_max_win.p, s.h_max_win.p, uint64_t(s.n_queries) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(s.ev_k0, st));
+    mcb200_dev_queries q{s.d_bases.p, s.d_seq_off.p, s.d_seq_query.p, s.d_max_win.p, s.n_seqs, s.n_queries, s.n_bases};
+    rc = mcb200_query_device(s.ws, &q, sk, s.d_top.p, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.ev_k1, st));
+    CU(cudaMemcpyAsync(s.h_top.p, s.d_top.p, uint64_t(s.n_queries) * b->maxc * sizeof(mcb200_candidate),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(s.ev_done, st));
+    return 0;
+}
+
+extern "C" int mcb200_batch_wait (mcb200_batch* b, uint32_t slot) {
+    CHECK_SLOT(b, slot);
+    Slot_& s = b->slots[slot];
+    if (!s.submitted) return fail(MCB200_ESTATE, "slot %u: nothing submitted", slot);
+    CU(cudaSetDevice(b->db->device));
+    CU(cudaEventSynchronize(s.ev_done));
+    if (!s.waited) {
+        cudaEventElapsedTime(&s.total_ms, s.ev_start, s.ev_done);
+        cudaEventElapsedTime(&s.kernels_ms, s.ev_k0, s.ev_k1);
+        s.waited = true;
+        if (s.n_queries) {
+            int err = 0;
+            CU(cudaMemcpy(&err, s.ws->error.p, sizeof(int), cudaMemcpyDeviceToHost));
+            if (err == 3) {
+                // a huge read outgrew the scratch pool: grow and redo this submit
+                CU(cudaMemset(s.ws->error.p, 0, sizeof(int)));
+                int rc = ensure_scratch(s.ws, s.ws->scratch_entries * 8);
+                if (rc) return rc;
+                const mcb200_sketching sk{s.ws->sk.k, s.ws->sk.s, s.ws->sk.w, s.ws->sk.stride};
+                s.waited = false;
+                rc = mcb200_batch_submit(b, slot, &sk);
+                if (rc) return rc;
+                return mcb200_batch_wait(b, slot);
+            }
+            if (err) return fail(MCB200_ECUDA, "device error flag %d", err);
+        }
+    }
+    return 0;
+}
+
+extern "C" int mcb200_batch_clear (mcb200_batch* b, uint32_t slot) {
+    CHECK_SLOT(b, slot);
+    Slot_& s = b->slots[slot];
+    if (s.submitted && !s.waited) { int rc = mcb200_batch_wait(b, slot); if (rc) return rc; }
+    s.n_queries = 0; s.n_seqs = 0; s.n_bases = 0; s.n_windows = 0;
+    s.submitted = false; s.waited = false;
+    return 0;
+}
+
+extern "C" uint32_t mcb200_batch_num_queries (const mcb200_batch* b, uint32_t slot) {
+    return (b && slot < b->slots.size()) ? b->slots[slot].n_queries : 0; }
+
+static int fetch_sketches (const mcb200_batch* cb, uint32_t slot) {
+    mcb200_batch* b = const_cast<mcb200_batch*>(cb);
+    Slot_& s = b->slots[slot];
+    if (s.sketches_fetched) return 0;
+    if (!s.submitted) return fail(MCB200_ESTATE, "nothing submitted");
+    int rc = mcb200_batch_wait(b, slot);
+    if (rc) return rc;
+    const uint32_t nw = mcb200_workspace_num_windows(s.ws);
+    s.n_windows = nw;
+    CU(s.h_feats.ensure(uint64_t(nw) * s.sub_s + 1));
+    CU(s.h_qry_win_off.ensure(uint64_t(s.sub_queries) + 1));
+    CU(cudaMemcpy(s.h_feats.p, s.ws->feats.p, uint64_t(nw) * s.sub_s * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(s.h_qry_win_off.p, s.ws->qry_win_off.p, (uint64_t(s.sub_queries) + 1) * 4, cudaMemcpyDeviceToHost));
+    s.sketches_fetched = true;
+    return 0;
+}
+
+extern "C" uint32_t mcb200_batch_num_windows (const mcb200_batch* b, uint32_t slot) {
+    if (!b || slot >= b->slots.size()) return 0;
+    if (!b->slots[slot].submitted || b->slots[slot].sub_queries == 0) return 0;
+    if (fetch_sketches(b, slot)) return 0;
+    return b->slots[slot].n_windows;
+}
+
+extern "C" const mcb200_candidate* mcb200_batch_top_candidates (const mcb200_batch* b, uint32_t slot,
+                                                                uint32_t query) {
+    if (!b || slot >= b->slots.size()) return nullptr;
+    const Slot_& s = b->slots[slot];
+    if (!s.waited || query >= s.sub_queries) return nullptr;
+    return s.h_top.p + uint64_t(query) * b->maxc;
+}
+
+extern "C" const uint64_t* mcb200_batch_allhits (const mcb200_batch* cb, uint32_t slot, uint32_t query,
+                                                 uint64_t* n) {
+    if (n) *n = 0;
+    if (!cb || slot >= cb->slots.size() || !cb->allhits) return nullptr;
+    mcb200_batch* b = const_cast<mcb200_batch*>(cb);
+    Slot_& s = b->slots[slot];
+    if (!s.waited || query >= s.sub_queries) return nullptr;
+    const uint32_t np = uint32_t(b->db->parts.size());
+    if (!s.allhits_fetched) {
+        cudaSetDevice(b->db->device);
+        const uint64_t cnt = uint64_t(s.sub_queries) * np + 1;
+        if (s.h_allhits_off.ensure(cnt) != cudaSuccess) return nullptr;
+        cudaMemcpy(s.h_allhits_off.p, s.ws->hit_offsets.p, cnt * 8, cudaMemcpyDeviceToHost);
+        const uint64_t total = s.h_allhits_off.p[cnt - 1];
+        if (s.h_allhits.ensure(total + 1) != cudaSuccess) return nullptr;
+        cudaMemcpy(s.h_allhits.p, s.ws->allhits.p, total * 8, cudaMemcpyDeviceToHost);
+        s.allhits_fetched = true;
+    }
+    const uint64_t b0 = s.h_allhits_off.p[uint64_t(query) * np], b1 = s.h_allhits_off.p[uint64_t(query + 1) * np];
+    if (n) *n = b1 - b0;
+    return s.h_allhits.p + b0;
+}
+
+extern "C" const uint32_t* mcb200_batch_sketch (const mcb200_batch* b, uint32_t slot, uint32_t window,
+                                                uint32_t* n) {
+    if (n) *n = 0;
+    if (!b || slot >= b->slots.size()) return nullptr;
+    if (fetch_sketches(b, slot)) return nullptr;
+    const Slot_& s = b->slots[slot];
+    if (window >= s.n_windows) return nullptr;
+    const uint32_t* f = s.h_feats.p + uint64_t(window) * s.sub_s;
+    uint32_t c = 0;
+    while (c < s.sub_s && f[c] != kNoFeature) ++c;
+    if (n) *n = c;
+    return f;
+}
+
+extern "C" uint32_t mcb200_batch_query_window_offset (const mcb200_batch* b, uint32_t slot, uint32_t query) {
+    if (!b || slot >= b->slots.size()) return 0;
+    if (fetch_sketches(b, slot)) return 0;
+    const Slot_& s = b->slots[slot];
+    if (query > s.sub_queries) return s.n_windows;
+    return s.h_qry_win_off.p[query];
+}
+
+extern "C" int mcb200_batch_last_timing (const mcb200_batch* b, uint32_t slot, float* total_ms,
+                                         float* kernels_ms) {
+    CHECK_SLOT(b, slot);
+    const Slot_& s = b->slots[slot];
+    if (!s.waited) return fail(MCB200_ESTATE, "slot %u: wait() first", slot);
+    if (total_ms) *total_ms = s.total_ms;
+    if (kernels_ms) *kernels_ms = s.kernels_ms;
+    return 0;
+}

@@ -1,0 +1,84 @@
+// Host-side declarations of the kernel launchers (one per .cu file).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/mcb200.h"
+#include "common.cuh"
+
+namespace mcb {
+
+extern unsigned long long g_launches;   // kernels launched by this library (api.cu)
+inline void count_launch (unsigned n = 1) { g_launches += n; }
+
+struct SketchParams { uint32_t k, s, w, stride; };
+
+// ---- kernels_sketch.cu ------------------------------------------------------
+// ASCII -> 2-bit codes (16 bases / u32, first base in the top bits) + ambiguity
+// bitmap (32 bases / u32, first base in the top bit).  n_bases_padded % 32 == 0.
+void launch_encode (const char* bases, uint64_t n_bases, uint32_t* codes, uint32_t* amb,
+                    cudaStream_t st);
+// per-sequence window counts (hash_dna.hpp:54-75)
+void launch_count_windows (const uint32_t* seq_off, uint32_t n_seqs, SketchParams p,
+                           uint32_t* seq_nwin, cudaStream_t st);
+// after the exclusive scan of seq_nwin into seq_win_off[n_seqs+1]:
+// win_seq[w] = owning sequence; qry_win_off[q] = first window of query q
+void launch_fill_windows (const uint32_t* seq_win_off, const uint32_t* seq_query, uint32_t n_seqs,
+                          uint32_t n_queries, uint32_t* win_seq, uint32_t* qry_win_off,
+                          cudaStream_t st);
+// window sketches: feats[w][s], ascending, padded with kNoFeature
+void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* seq_off,
+                    const uint32_t* seq_win_off, const uint32_t* win_seq, const uint32_t* d_nwin,
+                    SketchParams p, uint32_t* feats, int sm_count, cudaStream_t st);
+
+// ---- table.cu ---------------------------------------------------------------
+void launch_table_insert (Bucket* buckets, uint64_t nbuckets, const uint32_t* keys,
+                          const uint8_t* sizes, const uint64_t* offsets, const uint64_t* values,
+                          uint64_t nkeys, int* d_error, cudaStream_t st);
+// exclusive scan of u8 sizes -> u64 offsets (+base), device
+void device_scan_sizes (const uint8_t* sizes, uint64_t n, uint64_t base, uint64_t* offsets,
+                        void*& tmp, size_t& tmp_bytes, cudaStream_t st);
+void device_scan_u32 (const uint32_t* in, uint32_t* out, uint64_t n, void*& tmp, size_t& tmp_bytes,
+                      cudaStream_t st);
+void device_scan_u64 (const uint64_t* in, uint64_t* out, uint64_t n, void*& tmp, size_t& tmp_bytes,
+                      cudaStream_t st);
+// export: occupied slots in table order -> keys/sizes/value runs
+int  table_export (const Bucket* buckets, uint64_t nbuckets, const uint64_t* values,
+                   uint64_t nkeys, uint64_t nvalues, uint32_t* h_keys, uint8_t* h_sizes,
+                   uint64_t* h_values, cudaStream_t st);
+// build from (feature, location) pairs produced by sketching targets
+struct BuiltPart { uint32_t* keys; uint8_t* sizes; uint64_t* values; uint64_t nkeys, nvalues; };
+int  build_from_sketches (const uint32_t* feats, const uint32_t* win_seq, const uint32_t* seq_win_off,
+                          uint64_t nwin, uint32_t s, uint32_t first_target, uint32_t max_locations,
+                          BuiltPart& out, cudaStream_t st);
+
+// ---- kernels_query.cu -------------------------------------------------------
+struct QueryArgs {
+    const uint32_t* feats;        // [nwin][s]
+    const uint32_t* qry_win_off;  // [nq+1]
+    const uint32_t* max_win;      // [nq]
+    const uint64_t* tax_of_tgt;   // may be null
+    uint32_t        n_tax;        // entries in tax_of_tgt
+    uint32_t        nq, s, maxc;
+    TableView       table;
+    mcb200_candidate* top;        // [nq][maxc]
+    // all-hits output (optional)
+    uint64_t*       allhits;      // null if not wanted
+    const uint64_t* allhits_off;  // [nq+1] for this part
+    // heavy-query machinery
+    uint32_t*       heavy_list;   // [nq] query ids that overflowed the warp kernel
+    uint32_t*       heavy_count;  // [2]: [0] = appended, [1] = consumed (work queue)
+    uint64_t*       scratch;      // global scratch for huge queries (entries of 8 B + 4 B)
+    uint64_t        scratch_entries;
+    unsigned long long* scratch_cursor;
+    unsigned long long* counters; // [8] see mcb200_workspace_counters
+    int*            error;        // sticky device error flag
+};
+void launch_query_warp  (const QueryArgs& a, uint32_t cap, int sm_count, cudaStream_t st);
+void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st);
+// counts locations per query (for all-hits offsets)
+void launch_count_hits (const QueryArgs& a, uint64_t* counts, cudaStream_t st);
+void launch_merge_candidates (const mcb200_candidate* parts, uint32_t n_lists, uint32_t nq,
+                              uint32_t maxc, const uint64_t* tax_of_tgt, uint32_t n_tax,
+                              mcb200_candidate* out, cudaStream_t st);
+
+} // namespace mcb

@@ -1,0 +1,570 @@
+// Fused probe + per-read sort + contiguous-window candidate kernels (sm_100a).
+//
+// Reference behaviour restated (CPU semantics are the parity target):
+//   feature lookup, append bucket          host_hashmap.hpp:629-691, hash_multimap.hpp:1086-1098
+//   sort by (tgt,win), duplicates kept     query_handler.hpp:75-101, database.hpp:151-156
+//   for_all_contiguous_window_ranges       candidate_generation.hpp:47-108
+//   best_distinct_matches_...::insert      candidate_generation.hpp:172-231
+// What the GPU reference does in three kernels + bb_segsort through HBM
+// (gpu_hashmap_operations.cuh:847-942, query_batch.cu:542-633,
+// gpu_result_processing.cuh:325-473) is ONE kernel here: a warp owns a read,
+// gathers its locations into shared memory, sorts them there and reduces them
+// to the top candidates; only 16 B per candidate go back to HBM.
+//
+// Closed form used for the sliding window (equivalent to the reference's
+// two-pointer scan): with the read's locations sorted ascending as u64 keys
+// (tgt<<32|win), for entry j let f(j) = first index whose key >= (tgt_j<<32 |
+// max(win_j-W+1,0)); then hits(j) = j-f(j)+1 is the scan's `hits` when lst==j,
+// and the candidate of a target is the entry with the largest hits(j), smallest
+// j on ties (the scan only replaces on strictly greater).  Because j ascends
+// with tgt, "largest hits, smallest j" also realises the stable top-k order
+// (hits desc, arrival = target asc) of insert().
+#include "internal.h"
+
+namespace mcb {
+
+constexpr int      kQWarps   = 8;           // warps per CTA in the fused kernel
+constexpr int      kHeavyThreads = 256;
+constexpr uint32_t kMaxCand  = 32;          // candidates per query supported on device
+constexpr uint32_t kCounterSlots = 64;      // counters are spread over 64 slots x 8
+
+__device__ __forceinline__ uint32_t pow2_ceil (uint32_t x) {
+    return x <= 1 ? 1u : 1u << (32 - __clz(x - 1));
+}
+
+// first index in [0, n) with keys[idx] >= K  (keys ascending)
+template <class KeyPtr>
+__device__ __forceinline__ uint32_t lower_bound_u64 (KeyPtr keys, uint32_t n, uint64_t K) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < K) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint64_t window_floor_key (uint64_t key, uint32_t W) {
+    const uint32_t win = uint32_t(key);
+    const uint32_t lo = (win >= W - 1) ? win - (W - 1) : 0u;
+    return (key & 0xFFFFFFFF00000000ull) | lo;
+}
+
+__device__ __forceinline__ void write_empty (mcb200_candidate* top, uint32_t from, uint32_t maxc) {
+    for (uint32_t c = from; c < maxc; ++c) top[c] = mcb200_candidate{0xFFFFFFFFu, 0u, 0u, 0u};
+}
+
+// insert() with taxon merging, sequential (candidate_generation.hpp:172-231);
+// same restatement as oracle/mc_oracle.c:top_insert but written independently
+// for the device: `top`/`toptax` hold ntop entries sorted by hits desc.
+__device__ void insert_candidate (mcb200_candidate* top, uint64_t* toptax, uint32_t& ntop,
+                                  uint32_t maxc, mcb200_candidate c, uint64_t tax, bool merge_tax)
+{
+    if (ntop == maxc && top[ntop - 1].hits >= c.hits) return;
+    if (tax == 0) return;
+    if (merge_tax) {
+        for (uint32_t i = 0; i < ntop; ++i) {
+            if (toptax[i] != tax) continue;
+            if (c.hits > top[i].hits) {
+                top[i] = c;
+                while (i > 0 && top[i - 1].hits < top[i].hits) {
+                    const mcb200_candidate t = top[i - 1]; top[i - 1] = top[i]; top[i] = t;
+                    const uint64_t x = toptax[i - 1]; toptax[i - 1] = toptax[i]; toptax[i] = x;
+                    --i;
+                }
+            }
+            return;
+        }
+    }
+    uint32_t pos = 0;
+    while (pos < ntop && top[pos].hits >= c.hits) ++pos;
+    if (pos < ntop || ntop < maxc) {
+        const uint32_t last = (ntop < maxc) ? ntop : maxc - 1;
+        for (uint32_t j = last; j > pos; --j) { top[j] = top[j - 1]; toptax[j] = toptax[j - 1]; }
+        top[pos] = c; toptax[pos] = tax;
+        if (ntop < maxc) ++ntop;
+    }
+}
+
+// sequential candidate generation over a sorted list with cached hits(j);
+// one thread; used for `-lowest` above sequence (order dependent merge).
+template <class KeyPtr, class CntPtr>
+__device__ void sequential_candidates_tax (KeyPtr keys, CntPtr cnt, uint32_t H,
+                                           const uint64_t* tax_of_tgt, uint32_t n_tax,
+                                           mcb200_candidate* out, uint32_t maxc)
+{
+    mcb200_candidate top[kMaxCand];
+    uint64_t toptax[kMaxCand];
+    uint32_t ntop = 0;
+    uint32_t j = 0;
+    while (j < H) {
+        const uint32_t tgt = uint32_t(keys[j] >> 32);
+        uint32_t bc = 0, bj = j;
+        uint32_t e = j;
+        for (; e < H && uint32_t(keys[e] >> 32) == tgt; ++e) {
+            const uint32_t c = cnt[e];
+            if (c > bc) { bc = c; bj = e; }
+        }
+        const mcb200_candidate cand{tgt, bc, uint32_t(keys[bj - bc + 1]), uint32_t(keys[bj])};
+        const uint64_t tax = (tgt < n_tax) ? tax_of_tgt[tgt] : 0ull;
+        insert_candidate(top, toptax, ntop, maxc, cand, tax, true);
+        j = e;
+    }
+    for (uint32_t c = 0; c < ntop; ++c) out[c] = top[c];
+    write_empty(out, ntop, maxc);
+}
+
+// ---------------------------------------------------------------------------
+// fused warp kernel
+// ---------------------------------------------------------------------------
+struct WarpSmem {
+    uint64_t* keys;     // [cap]
+    uint32_t* cnt;      // [cap]
+    uint64_t* sdata;    // [32]
+    uint32_t* sbase;    // [33]
+    uint32_t* chosen;   // [kMaxCand]
+};
+
+__host__ __device__ inline size_t warp_smem_bytes (uint32_t cap) {
+    return size_t(cap) * 12 + 32 * 8 + 36 * 4 + kMaxCand * 4;
+}
+
+template <bool kTax>
+__global__ void __launch_bounds__(kQWarps * 32)
+query_warp_kernel (QueryArgs a, uint32_t cap)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ unsigned long long s_counters[4];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
+    __syncthreads();
+
+    uint8_t* mine = smem_raw + warp * warp_smem_bytes(cap);
+    WarpSmem sm;
+    sm.keys   = reinterpret_cast<uint64_t*>(mine);
+    sm.sdata  = sm.keys + cap;
+    sm.cnt    = reinterpret_cast<uint32_t*>(sm.sdata + 32);
+    sm.sbase  = sm.cnt + cap;
+    sm.chosen = sm.sbase + 36;
+
+    const uint32_t q = blockIdx.x * kQWarps + warp;
+    uint32_t sectors = 0, nfeat = 0, H = 0;
+    bool fused = false;
+    if (q < a.nq) {
+        const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
+        const uint32_t nslots = (w1 - w0) * a.s;
+        const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+        mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
+        bool overflow = false;
+
+        // ---- probe + gather ------------------------------------------------
+        for (uint32_t c = 0; c < nslots; c += 32) {
+            const uint32_t idx = c + lane;
+            const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
+            uint32_t size = 0; uint64_t data = 0;
+            if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
+            const uint32_t incl = warp_incl_scan(size);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            if (total == 0) continue;
+            if (H + total > cap) { overflow = true; break; }
+            sm.sbase[lane] = H + incl - size;
+            sm.sdata[lane] = data;
+            if (lane == 31) sm.sbase[32] = H + total;
+            __syncwarp();
+            for (uint32_t p = H + lane; p < H + total; p += 32) {
+                // last b with sbase[b] <= p
+                uint32_t b = 0;
+                #pragma unroll
+                for (uint32_t step = 16; step > 0; step >>= 1)
+                    if (sm.sbase[b + step] <= p) b += step;
+                const uint32_t sb = sm.sbase[b];
+                const uint32_t sz = sm.sbase[b + 1] - sb;
+                const uint64_t d = sm.sdata[b];
+                sm.keys[p] = (sz == 1) ? d : __ldg(a.table.values + d + (p - sb));
+            }
+            __syncwarp();
+            H += total;
+        }
+
+        if (overflow) {
+            if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+        } else if (H == 0) {
+            fused = true;
+            if (lane == 0) write_empty(top, 0, a.maxc);
+        } else {
+            fused = true;
+            // ---- bitonic sort in shared memory ------------------------------
+            const uint32_t n = max(pow2_ceil(H), 2u);
+            for (uint32_t i = H + lane; i < n; i += 32) sm.keys[i] = kPadKey;
+            __syncwarp();
+            for (uint32_t k = 2; k <= n; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < (n >> 1); i += 32) {
+                        const uint32_t x = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                        const uint32_t y = x | j;
+                        const uint64_t ka = sm.keys[x], kb = sm.keys[y];
+                        const bool up = (x & k) == 0;
+                        if ((ka > kb) == up) { sm.keys[x] = kb; sm.keys[y] = ka; }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (a.allhits) {
+                uint64_t* dst = a.allhits + a.allhits_off[q];
+                for (uint32_t i = lane; i < H; i += 32) dst[i] = sm.keys[i];
+            }
+            // ---- hits(j) for every entry ---------------------------------------
+            const uint32_t W = __ldg(a.max_win + q);
+            uint32_t best_c = 0, best_j = 0xFFFFFFFFu;
+            for (uint32_t j = lane; j < H; j += 32) {
+                uint32_t c = 1;
+                if (W > 0) {
+                    const uint64_t K = window_floor_key(sm.keys[j], W);
+                    c = j - lower_bound_u64(sm.keys, j, K) + 1;
+                }
+                sm.cnt[j] = c;
+                if (c > best_c) { best_c = c; best_j = j; }
+            }
+            __syncwarp();
+            if (kTax) {
+                if (lane == 0)
+                    sequential_candidates_tax(sm.keys, sm.cnt, H, a.tax_of_tgt, a.n_tax, top, a.maxc);
+            } else {
+                // ---- top-k distinct targets ----------------------------------
+                uint32_t c = 0;
+                for (; c < a.maxc; ++c) {
+                    if (c > 0) {
+                        best_c = 0; best_j = 0xFFFFFFFFu;
+                        for (uint32_t j = lane; j < H; j += 32) {
+                            const uint32_t tgt = uint32_t(sm.keys[j] >> 32);
+                            bool taken = false;
+                            for (uint32_t i = 0; i < c; ++i) taken |= (sm.chosen[i] == tgt);
+                            const uint32_t cj = sm.cnt[j];
+                            if (!taken && cj > best_c) { best_c = cj; best_j = j; }
+                        }
+                    }
+                    const uint32_t wmax = __reduce_max_sync(kFull, best_c);
+                    if (wmax == 0) break;
+                    const uint32_t wj = __reduce_min_sync(kFull, best_c == wmax ? best_j : 0xFFFFFFFFu);
+                    const uint64_t ke = sm.keys[wj];
+                    if (lane == 0) {
+                        top[c] = mcb200_candidate{uint32_t(ke >> 32), wmax,
+                                                  uint32_t(sm.keys[wj - wmax + 1]), uint32_t(ke)};
+                        sm.chosen[c] = uint32_t(ke >> 32);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) write_empty(top, c, a.maxc);
+            }
+        }
+    }
+    // ---- statistics ---------------------------------------------------------
+    if (a.counters) {
+        const uint32_t sec = __reduce_add_sync(kFull, sectors);
+        const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
+        if (lane == 0) {
+            if (fused) atomicAdd(&s_counters[0], 1ull);
+            if (fused) atomicAdd(&s_counters[1], (unsigned long long)H);
+            atomicAdd(&s_counters[2], (unsigned long long)nf);
+            atomicAdd(&s_counters[3], (unsigned long long)sec);
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            // counters: [0] fused queries [3] locations [4] features [5] sectors
+            const int dst = threadIdx.x == 0 ? 0 : 2 + threadIdx.x;
+            atomicAdd(a.counters + (blockIdx.x % kCounterSlots) * 8 + dst, s_counters[threadIdx.x]);
+        }
+    }
+}
+
+void launch_query_warp (const QueryArgs& a, uint32_t cap, int, cudaStream_t st)
+{
+    if (!a.nq) return;
+    const size_t smem = warp_smem_bytes(cap) * kQWarps;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
+    if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, cap);
+    else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, cap);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// heavy queries: one CTA per query, shared memory if it fits, else global scratch
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_excl_scan (uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, t = 0;
+    #pragma unroll
+    for (int i = 0; i < kHeavyThreads / 32; ++i) {
+        const uint32_t x = s_warp[i];
+        if (i < int(warp)) woff += x;
+        t += x;
+    }
+    total = t;
+    __syncthreads();
+    return woff + incl - v;
+}
+
+template <class KeyPtr>
+__device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (n >> 1); i += kHeavyThreads) {
+                const uint32_t x = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const uint32_t y = x | j;
+                const uint64_t ka = keys[x], kb = keys[y];
+                const bool up = (x & k) == 0;
+                if ((ka > kb) == up) { keys[x] = kb; keys[y] = ka; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kHeavyThreads)
+query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_base[kHeavyThreads + 1];
+    __shared__ uint64_t s_data[kHeavyThreads];
+    __shared__ uint32_t s_warp[kHeavyThreads / 32];
+    __shared__ uint32_t s_chosen[kMaxCand];
+    __shared__ uint32_t s_red_c[kHeavyThreads / 32], s_red_j[kHeavyThreads / 32];
+    __shared__ uint32_t s_q, s_bc;
+    __shared__ unsigned long long s_goff;
+    __shared__ unsigned long long s_cnt[4];
+
+    uint64_t* sh_keys = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* sh_cnt  = reinterpret_cast<uint32_t*>(sh_keys + cap_smem);
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    if (tid < 4) s_cnt[tid] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t i = atomicAdd(a.heavy_count + 1, 1u);
+            s_q = (i < *reinterpret_cast<volatile uint32_t*>(a.heavy_count)) ? a.heavy_list[i] : 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q == 0xFFFFFFFFu) break;
+
+        const uint32_t w0 = a.qry_win_off[q], w1 = a.qry_win_off[q + 1];
+        const uint32_t nslots = (w1 - w0) * a.s;
+        const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+        mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
+        uint32_t sectors = 0, nfeat = 0;
+
+        // ---- pass 1: total number of locations -----------------------------
+        uint32_t mysum = 0;
+        for (uint32_t idx = tid; idx < nslots; idx += kHeavyThreads) {
+            const uint32_t f = fbase[idx];
+            if (f != kNoFeature) { uint64_t d; mysum += table_find(a.table, f, d, sectors); ++nfeat; }
+        }
+        uint32_t H = 0;
+        block_excl_scan(mysum, s_warp, H);
+        if (H == 0) { if (tid == 0) write_empty(top, 0, a.maxc); continue; }
+        const uint32_t n = max(pow2_ceil(H), 2u);
+
+        uint64_t* keys; uint32_t* cnt;
+        if (n <= cap_smem) { keys = sh_keys; cnt = sh_cnt; }
+        else {
+            if (tid == 0) s_goff = atomicAdd(a.scratch_cursor, (unsigned long long)n);
+            __syncthreads();
+            const unsigned long long off = s_goff;
+            if (off + n > a.scratch_entries) {            // host grows the pool and retries
+                if (tid == 0) { atomicExch(a.error, 3); write_empty(top, 0, a.maxc); }
+                continue;
+            }
+            keys = a.scratch + off;
+            cnt  = reinterpret_cast<uint32_t*>(a.scratch + a.scratch_entries) + off;
+        }
+
+        // ---- pass 2: gather, 256 feature slots at a time -------------------
+        uint32_t filled = 0;
+        for (uint32_t c = 0; c < nslots; c += kHeavyThreads) {
+            const uint32_t idx = c + tid;
+            const uint32_t f = (idx < nslots) ? fbase[idx] : kNoFeature;
+            uint32_t size = 0; uint64_t data = 0;
+            if (f != kNoFeature) { uint32_t sx = 0; size = table_find(a.table, f, data, sx); }
+            uint32_t total = 0;
+            const uint32_t excl = block_excl_scan(size, s_warp, total);
+            s_base[tid] = filled + excl;
+            s_data[tid] = data;
+            if (tid == kHeavyThreads - 1) s_base[kHeavyThreads] = filled + total;
+            __syncthreads();
+            for (uint32_t p = filled + tid; p < filled + total; p += kHeavyThreads) {
+                uint32_t b = 0;
+                #pragma unroll
+                for (uint32_t step = kHeavyThreads / 2; step > 0; step >>= 1)
+                    if (s_base[b + step] <= p) b += step;
+                const uint32_t sb = s_base[b];
+                const uint32_t sz = s_base[b + 1] - sb;
+                const uint64_t d = s_data[b];
+                keys[p] = (sz == 1) ? d : a.table.values[d + (p - sb)];
+            }
+            __syncthreads();
+            filled += total;
+        }
+        for (uint32_t i = H + tid; i < n; i += kHeavyThreads) keys[i] = kPadKey;
+        __syncthreads();
+
+        block_bitonic_sort(keys, n);
+
+        if (a.allhits) {
+            uint64_t* dst = a.allhits + a.allhits_off[q];
+            for (uint32_t i = tid; i < H; i += kHeavyThreads) dst[i] = keys[i];
+        }
+
+        // ---- hits(j) ---------------------------------------------------------
+        const uint32_t W = a.max_win[q];
+        for (uint32_t j = tid; j < H; j += kHeavyThreads) {
+            uint32_t c = 1;
+            if (W > 0) c = j - lower_bound_u64(keys, j, window_floor_key(keys[j], W)) + 1;
+            cnt[j] = c;
+        }
+        __syncthreads();
+
+        if (a.tax_of_tgt) {
+            if (tid == 0) sequential_candidates_tax(keys, cnt, H, a.tax_of_tgt, a.n_tax, top, a.maxc);
+        } else {
+            uint32_t c = 0;
+            for (; c < a.maxc; ++c) {
+                uint32_t best_c = 0, best_j = 0xFFFFFFFFu;
+                for (uint32_t j = tid; j < H; j += kHeavyThreads) {
+                    const uint32_t tgt = uint32_t(keys[j] >> 32);
+                    bool taken = false;
+                    for (uint32_t i = 0; i < c; ++i) taken |= (s_chosen[i] == tgt);
+                    const uint32_t cj = cnt[j];
+                    if (!taken && cj > best_c) { best_c = cj; best_j = j; }
+                }
+                const uint32_t wmax = __reduce_max_sync(kFull, best_c);
+                const uint32_t wj = __reduce_min_sync(kFull, best_c == wmax ? best_j : 0xFFFFFFFFu);
+                if (lane == 0) { s_red_c[warp] = wmax; s_red_j[warp] = wj; }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t bc = 0, bj = 0xFFFFFFFFu;
+                    for (int i = 0; i < kHeavyThreads / 32; ++i)
+                        if (s_red_c[i] > bc || (s_red_c[i] == bc && s_red_j[i] < bj)) { bc = s_red_c[i]; bj = s_red_j[i]; }
+                    s_bc = bc;
+                    if (bc > 0) {
+                        const uint64_t ke = keys[bj];
+                        top[c] = mcb200_candidate{uint32_t(ke >> 32), bc, uint32_t(keys[bj - bc + 1]), uint32_t(ke)};
+                        s_chosen[c] = uint32_t(ke >> 32);
+                    }
+                }
+                __syncthreads();
+                if (s_bc == 0) break;
+            }
+            if (tid == 0) write_empty(top, c, a.maxc);
+        }
+
+        if (a.counters) {
+            const uint32_t sec = __reduce_add_sync(kFull, sectors);
+            const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
+            if (lane == 0) {
+                atomicAdd(&s_cnt[2], (unsigned long long)nf);
+                atomicAdd(&s_cnt[3], (unsigned long long)sec);
+            }
+            if (tid == 0) {
+                atomicAdd(&s_cnt[n <= cap_smem ? 0 : 1], 1ull);
+                atomicAdd(a.counters + (blockIdx.x % kCounterSlots) * 8 + 3, (unsigned long long)H);
+            }
+        }
+    }
+    __syncthreads();
+    if (a.counters && tid < 4) {
+        // [1] CTA-kernel queries in smem, [2] in global scratch, [4] features, [5] sectors
+        const int dst = tid == 0 ? 1 : (tid == 1 ? 2 : 2 + tid);
+        atomicAdd(a.counters + (blockIdx.x % kCounterSlots) * 8 + dst, s_cnt[tid]);
+    }
+}
+
+constexpr uint32_t kHeavySmemEntries = 16384;   // 16384 * 12 B = 192 KB
+
+void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
+{
+    static bool attr_set = false;
+    const size_t smem = size_t(kHeavySmemEntries) * 12;
+    if (!attr_set) {
+        cudaFuncSetAttribute(query_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr_set = true;
+    }
+    query_heavy_kernel<<<sm_count, kHeavyThreads, smem, st>>>(a, kHeavySmemEntries);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// number of locations per query (all-hits offsets)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+count_hits_kernel (QueryArgs a, uint64_t* __restrict__ counts)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= a.nq) return;
+    const uint32_t w0 = a.qry_win_off[q], w1 = a.qry_win_off[q + 1];
+    const uint32_t nslots = (w1 - w0) * a.s;
+    const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+    uint32_t sum = 0, sectors = 0;
+    for (uint32_t idx = lane; idx < nslots; idx += 32) {
+        const uint32_t f = fbase[idx];
+        if (f != kNoFeature) { uint64_t d; sum += table_find(a.table, f, d, sectors); }
+    }
+    sum = __reduce_add_sync(kFull, sum);
+    if (lane == 0) counts[q] = sum;
+}
+
+void launch_count_hits (const QueryArgs& a, uint64_t* counts, cudaStream_t st)
+{
+    if (!a.nq) return;
+    count_hits_kernel<<<(a.nq + 7) / 8, 256, 0, st>>>(a, counts);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// stable part-ordered merge of candidate lists, one thread per query
+// ---------------------------------------------------------------------------
+__global__ void merge_candidates_kernel (const mcb200_candidate* __restrict__ parts, uint32_t n_lists,
+                                         uint32_t nq, uint32_t maxc,
+                                         const uint64_t* __restrict__ tax_of_tgt, uint32_t n_tax,
+                                         mcb200_candidate* __restrict__ out)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    mcb200_candidate top[kMaxCand];
+    uint64_t toptax[kMaxCand];
+    uint32_t ntop = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) {
+        const mcb200_candidate* src = parts + (uint64_t(l) * nq + q) * maxc;
+        for (uint32_t i = 0; i < maxc; ++i) {
+            const mcb200_candidate c = src[i];
+            if (c.hits == 0) break;
+            uint64_t tax = uint64_t(c.tgt) + 1;
+            if (tax_of_tgt) tax = (c.tgt < n_tax) ? tax_of_tgt[c.tgt] : 0ull;
+            insert_candidate(top, toptax, ntop, maxc, c, tax, tax_of_tgt != nullptr);
+        }
+    }
+    mcb200_candidate* dst = out + uint64_t(q) * maxc;
+    for (uint32_t c = 0; c < ntop; ++c) dst[c] = top[c];
+    write_empty(dst, ntop, maxc);
+}
+
+void launch_merge_candidates (const mcb200_candidate* parts, uint32_t n_lists, uint32_t nq,
+                              uint32_t maxc, const uint64_t* tax_of_tgt, uint32_t n_tax,
+                              mcb200_candidate* out, cudaStream_t st)
+{
+    if (!nq) return;
+    merge_candidates_kernel<<<(nq + 127) / 128, 128, 0, st>>>(parts, n_lists, nq, maxc, tax_of_tgt,
+                                                              n_tax, out);
+    count_launch();
+}
+
+} // namespace mcb

@@ -1,0 +1,293 @@
+// Encode + window tables + min-hash sketch kernels (sm_100a).
+//
+// Reference behaviour restated:
+//   for_each_window                      hash_dna.hpp:54-75
+//   for_each_kmer_2bit (+ambiguity)      dna_encoding.hpp:270-316
+//   unambiguous canonical k-mers         dna_encoding.hpp:433-444
+//   single_function_unique_min_hasher    hash_dna.hpp:207-255
+// The GPU reference does this with a 128-key bitonic sort per warp
+// (gpu_hashmap_operations.cuh:178-453); here the s smallest unique hashes are
+// selected with s hardware warp-min reductions (REDUX) instead of a full sort,
+// and the packed bases are staged into shared memory with 1-D bulk async
+// copies (TMA engine) one tile ahead of the math.
+#include "internal.h"
+
+namespace mcb {
+
+// ---------------------------------------------------------------------------
+// encode: 32 bases per thread, two 128-bit loads, one 2x32-bit + one 32-bit store
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void encode4 (uint32_t word, uint32_t& codes, uint32_t& amb) {
+    // word = 4 ASCII chars, first char in the low byte
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t c = (word >> (8 * i)) & 0xDFu;       // fold lower case
+        const uint32_t v = (c >> 1) & 3u;                   // A0 C1 T2 G3 (U like T)
+        const uint32_t code = v ^ (v >> 1);                 // A0 C1 G2 T3
+        const uint32_t d = c - 0x41u;                       // 'A'
+        // valid letters: A(0) C(2) G(6) T(19) U(20)
+        const uint32_t ok = (d < 32u) ? ((0x00180045u >> d) & 1u) : 0u;
+        codes = (codes << 2) | (ok ? code : 0u);
+        amb   = (amb << 1) | (ok ^ 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+encode_kernel (const uint8_t* __restrict__ bases, uint64_t n_bases,
+               uint32_t* __restrict__ codes, uint32_t* __restrict__ amb, uint64_t n_units)
+{
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n_units) return;
+    const uint64_t p = t * 32;
+    uint32_t w[8];
+    if (p + 32 <= n_bases) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bases + p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(bases + p + 16));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t x = 0;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t q = p + 4 * i + j;
+                const uint32_t c = (q < n_bases) ? bases[q] : 0u;   // 0 = ambiguous
+                x |= c << (8 * j);
+            }
+            w[i] = x;
+        }
+    }
+    uint32_t c0 = 0, c1 = 0, am = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) encode4(w[i], c0, am);
+    #pragma unroll
+    for (int i = 4; i < 8; ++i) encode4(w[i], c1, am);
+    reinterpret_cast<uint2*>(codes)[t] = make_uint2(c0, c1);
+    amb[t] = am;
+}
+
+void launch_encode (const char* bases, uint64_t n_bases, uint32_t* codes, uint32_t* amb,
+                    cudaStream_t st)
+{
+    const uint64_t units = (n_bases + 31) / 32;
+    if (!units) return;
+    encode_kernel<<<unsigned((units + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(bases), n_bases, codes, amb, units);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// window tables
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t num_windows (uint32_t len, uint32_t w, uint32_t stride) {
+    if (len <= w) return 1;
+    const uint32_t full = (len - w) / stride + 1;
+    return full + ((uint64_t(full) * stride < len) ? 1u : 0u);
+}
+
+__global__ void count_windows_kernel (const uint32_t* __restrict__ seq_off, uint32_t n_seqs,
+                                      SketchParams p, uint32_t* __restrict__ seq_nwin)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seqs) return;
+    seq_nwin[i] = num_windows(seq_off[i + 1] - seq_off[i], p.w, p.stride);
+}
+
+void launch_count_windows (const uint32_t* seq_off, uint32_t n_seqs, SketchParams p,
+                           uint32_t* seq_nwin, cudaStream_t st)
+{
+    if (!n_seqs) return;
+    count_windows_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(seq_off, n_seqs, p, seq_nwin);
+    count_launch();
+}
+
+__global__ void fill_windows_kernel (const uint32_t* __restrict__ seq_win_off,
+                                     const uint32_t* __restrict__ seq_query, uint32_t n_seqs,
+                                     uint32_t n_queries, uint32_t* __restrict__ win_seq,
+                                     uint32_t* __restrict__ qry_win_off)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seqs) return;
+    const uint32_t b = seq_win_off[i], e = seq_win_off[i + 1];
+    for (uint32_t w = b; w < e; ++w) win_seq[w] = i;
+    const uint32_t q = seq_query[i];
+    if (i == 0 || seq_query[i - 1] != q) qry_win_off[q] = b;
+    if (i == n_seqs - 1) qry_win_off[n_queries] = e;
+}
+
+void launch_fill_windows (const uint32_t* seq_win_off, const uint32_t* seq_query, uint32_t n_seqs,
+                          uint32_t n_queries, uint32_t* win_seq, uint32_t* qry_win_off,
+                          cudaStream_t st)
+{
+    if (!n_seqs) return;
+    fill_windows_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(seq_win_off, seq_query, n_seqs,
+                                                              n_queries, win_seq, qry_win_off);
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------
+// sketch: one warp per window, persistent CTAs, double-buffered bulk copies
+// ---------------------------------------------------------------------------
+constexpr int kSketchThreads = 256;
+constexpr int kSketchWarps   = kSketchThreads / 32;
+constexpr uint32_t kAlignBases = 128;    // 32 B of codes, 16 B of ambiguity bits
+constexpr uint32_t kSlackBases = 64;     // lanes read up to 2 words past the last base
+
+struct WinDesc { uint32_t start; uint32_t n; };   // absolute base index, length
+
+__device__ __forceinline__ WinDesc window_desc (uint32_t w, const uint32_t* __restrict__ seq_off,
+                                                const uint32_t* __restrict__ seq_win_off,
+                                                const uint32_t* __restrict__ win_seq,
+                                                const SketchParams& p)
+{
+    const uint32_t sq  = __ldg(win_seq + w);
+    const uint32_t j   = w - __ldg(seq_win_off + sq);
+    const uint32_t so  = __ldg(seq_off + sq);
+    const uint32_t len = __ldg(seq_off + sq + 1) - so;
+    WinDesc d;
+    if (len <= p.w) { d.start = so; d.n = len; }
+    else {
+        const uint32_t b = j * p.stride;
+        d.start = so + b;
+        d.n = (b + p.w <= len) ? p.w : (len - b);
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(kSketchThreads)
+sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ amb,
+               const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_win_off,
+               const uint32_t* __restrict__ win_seq, const uint32_t* __restrict__ d_nwin,
+               SketchParams p, uint32_t* __restrict__ feats,
+               uint32_t tile_windows, uint32_t stage_bases)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // [stage0 codes][stage1 codes][stage0 amb][stage1 amb][desc0][desc1][base0,base1][bars]
+    uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_amb   = s_codes + 2 * (stage_bases / 16);
+    WinDesc*  s_desc  = reinterpret_cast<WinDesc*>(s_amb + 2 * (stage_bases / 32));
+    uint32_t* s_base  = reinterpret_cast<uint32_t*>(s_desc + 2 * tile_windows);
+    uint64_t* s_bar   = reinterpret_cast<uint64_t*>(s_base + 2);
+
+    const uint32_t nwin   = *d_nwin;
+    const uint32_t ntiles = (nwin + tile_windows - 1) / tile_windows;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    auto make_desc = [&] (uint32_t tile, uint32_t stage) {
+        const uint32_t w0 = tile * tile_windows;
+        for (uint32_t i = tid; i < tile_windows; i += kSketchThreads) {
+            const uint32_t w = w0 + i;
+            WinDesc d{0, 0};
+            if (w < nwin) d = window_desc(w, seq_off, seq_win_off, win_seq, p);
+            s_desc[stage * tile_windows + i] = d;
+        }
+    };
+    auto issue_copy = [&] (uint32_t tile, uint32_t stage) {   // thread 0 only
+        const uint32_t w0 = tile * tile_windows;
+        const uint32_t cnt = min(tile_windows, nwin - w0);
+        const WinDesc f = s_desc[stage * tile_windows];
+        const WinDesc l = s_desc[stage * tile_windows + cnt - 1];
+        const uint32_t lo = f.start & ~(kAlignBases - 1);
+        uint32_t hi = (l.start + l.n + kSlackBases + kAlignBases - 1) & ~(kAlignBases - 1);
+        if (hi - lo > stage_bases) hi = lo + stage_bases;      // never exceeds by construction
+        const uint32_t cb = (hi - lo) / 4, ab = (hi - lo) / 8;
+        s_base[stage] = lo;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[stage], cb + ab);
+        bulk_g2s(s_codes + stage * (stage_bases / 16), codes + lo / 16, cb, &s_bar[stage]);
+        bulk_g2s(s_amb + stage * (stage_bases / 32), amb + lo / 32, ab, &s_bar[stage]);
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tile < ntiles) {
+        make_desc(tile, 0);
+        __syncthreads();
+        if (tid == 0) issue_copy(tile, 0);
+    }
+    const uint32_t kshift = 32u - 2u * p.k;
+    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t cur = it & 1u, nxt = cur ^ 1u;
+        const uint32_t next_tile = tile + gridDim.x;
+        if (next_tile < ntiles) make_desc(next_tile, nxt);
+        __syncthreads();
+        if (tid == 0 && next_tile < ntiles) issue_copy(next_tile, nxt);
+        mbar_wait(&s_bar[cur], (it >> 1) & 1u);
+
+        const uint32_t* sc = s_codes + cur * (stage_bases / 16);
+        const uint32_t* sa = s_amb + cur * (stage_bases / 32);
+        const uint32_t base = s_base[cur];
+        const uint32_t w0 = tile * tile_windows;
+        const uint32_t cnt = min(tile_windows, nwin - w0);
+
+        for (uint32_t i = warp; i < cnt; i += kSketchWarps) {
+            const WinDesc d = s_desc[cur * tile_windows + i];
+            const uint32_t nk = (d.n >= p.k) ? (d.n - p.k + 1) : 0u;
+            const uint32_t s_eff = min(p.s, nk);
+            uint32_t run = kNoFeature;
+            for (uint32_t q0 = 0; q0 < nk; q0 += 128) {
+                const uint32_t q   = q0 + 4 * lane;          // first k-mer of this lane
+                const uint32_t rel = d.start + q - base;
+                uint32_t v[4] = {kNoFeature, kNoFeature, kNoFeature, kNoFeature};
+                if (q < nk) {
+                    const uint32_t wi = rel >> 4, o = rel & 15u;
+                    const uint32_t W0 = sc[wi], W1 = sc[wi + 1], W2 = sc[wi + 2];
+                    const uint32_t ai = rel >> 5, ao = rel & 31u;
+                    const uint32_t A  = __funnelshift_l(sa[ai + 1], sa[ai], ao);
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t oj = o + j;
+                        const uint32_t x = (oj < 16u) ? __funnelshift_l(W1, W0, 2 * oj)
+                                                      : __funnelshift_l(W2, W1, 2 * (oj - 16u));
+                        const uint32_t kmer = x >> kshift;
+                        const uint32_t ambig = (A << j) >> (32u - p.k);
+                        if (q + j < nk && ambig == 0) v[j] = hash32(canonical32(kmer, p.k));
+                    }
+                }
+                // s smallest unique values of {v[0..3] of all lanes} U {run of all lanes}
+                uint32_t newrun = kNoFeature;
+                for (uint32_t r = 0; r < s_eff; ++r) {
+                    const uint32_t m = min(min(min(v[0], v[1]), min(v[2], v[3])), run);
+                    const uint32_t wm = __reduce_min_sync(kFull, m);
+                    if (wm == kNoFeature) break;
+                    if (lane == r) newrun = wm;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = (v[j] == wm) ? kNoFeature : v[j];
+                    run = (run == wm) ? kNoFeature : run;
+                }
+                run = newrun;
+            }
+            if (lane < p.s) feats[uint64_t(w0 + i) * p.s + lane] = run;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* seq_off,
+                    const uint32_t* seq_win_off, const uint32_t* win_seq, const uint32_t* d_nwin,
+                    SketchParams p, uint32_t* feats, int sm_count, cudaStream_t st)
+{
+    // tile: as many windows as fit a ~24 KB stage, at most 64
+    uint32_t tile_windows = 64;
+    while (tile_windows > kSketchWarps && uint64_t(tile_windows) * p.w > 96 * 1024) tile_windows /= 2;
+    uint32_t stage_bases = tile_windows * p.w + kAlignBases + kSlackBases + kAlignBases;
+    stage_bases = (stage_bases + kAlignBases - 1) & ~(kAlignBases - 1);
+    const size_t smem = 2 * (stage_bases / 4) + 2 * (stage_bases / 8)
+                      + 2 * tile_windows * sizeof(WinDesc) + 2 * sizeof(uint32_t) + 8
+                      + 2 * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int grid = sm_count * 4;
+    sketch_kernel<<<grid, kSketchThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
+                                                      d_nwin, p, feats, tile_windows, stage_bases);
+    count_launch();
+}
+
+} // namespace mcb

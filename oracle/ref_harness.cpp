@@ -16,7 +16,8 @@
  * It also serves as the CPU baseline for bench.py (hot path only, T threads).
  *
  * usage: mc_ref_harness <db> <reads.txt> <out.bin|-> [key=value ...]
- *   reads.txt : one query per line, "SEQ1" or "SEQ1 SEQ2" (paired)
+ *   reads.txt : one query per line, "SEQ1" or "SEQ1 SEQ2" (paired); the token
+ *               "-" stands for an empty sequence
  *   keys      : maxcand=2 insert=0 part=-1 threads=1 repeat=1 sketches=1
  *               allhits=1
  * output (all u32 LE):
@@ -52,6 +53,7 @@ struct seq_query {            // what make_candidate_generation_rules needs
 
 sequence to_seq (const std::string& s, size_t b, size_t e) {
     sequence q;
+    if (e - b == 1 && s[b] == '-') return q;
     q.resize(e - b);
     if (e > b) memcpy(q.data(), s.data() + b, e - b);
     return q;

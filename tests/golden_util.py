@@ -1,0 +1,57 @@
+"""Loaders for tests/golden/*.npz (made by oracle/make_golden.py from the reference)."""
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+C1 = os.path.join(ROOT, "oracle", "_ref", "c1")
+
+
+def _ragged(flat, off):
+    return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+class Expected:
+    """reference outputs for one harness run: per read sketches / allhits / top"""
+
+    def __init__(self, z, prefix):
+        feats, off, cnt = z[prefix + "sk_feats"], z[prefix + "sk_off"], z[prefix + "sk_cnt"]
+        sk = _ragged(feats, off)
+        self.sketches, p = [], 0
+        for c in cnt:
+            self.sketches.append(sk[p:p + c])
+            p += c
+        self.allhits = _ragged(z[prefix + "allhits"], z[prefix + "allhits_off"])
+        top, toff = z[prefix + "top"], z[prefix + "top_off"]
+        self.top = [[tuple(int(x) for x in row) for row in top[toff[i]:toff[i + 1]]] for i in range(len(toff) - 1)]
+
+
+class G1:
+    def __init__(self):
+        z = np.load(os.path.join(GOLD, "g1.npz"))
+        self.z = z
+        self.keys, self.sizes, self.values = z["keys"], z["sizes"], z["values"]
+        self.k, self.s, self.w, self.stride = (int(x) for x in z["sketching"])
+        r1 = _ragged(z["reads1"], z["reads1_off"])
+        r2 = _ragged(z["reads2"], z["reads2_off"])
+        self.reads = [(a.tobytes(), b.tobytes()) for a, b in zip(r1, r2)]
+        self.targets = [t.tobytes() for t in _ragged(z["targets"], z["targets_off"])]
+        self.target_windows = z["target_windows"]
+
+    def expected(self, tag):
+        return Expected(self.z, tag)
+
+
+class G2:
+    def __init__(self):
+        z = np.load(os.path.join(GOLD, "g2.npz"))
+        self.z = z
+        self.parts = [(z[f"p{p}_keys"], z[f"p{p}_sizes"], z[f"p{p}_values"]) for p in (0, 1)]
+
+    def expected(self, part):
+        return Expected(self.z, f"p{part}_")
+
+
+def kat():
+    return np.load(os.path.join(GOLD, "kat.npz"))

@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden fixtures produced by
+the reference itself, the oracle on seeded inputs, and the reference's own golden file."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden_util import C1, G1, G2, kat
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g1():
+    from metacache_b200.database import Database
+    g = G1()
+    g.db = Database(0, 1)
+    g.db.load_part_arrays(0, g.keys, g.sizes, g.values, batch=50000)   # several append batches
+    yield g
+    g.db.close()
+
+
+def _sk(g):
+    from metacache_b200.database import SketchingOpt
+    return SketchingOpt(g.k, g.s, g.w, g.stride)
+
+
+def test_kat_sketches_on_gpu(g1):
+    from metacache_b200.database import query_reads
+    z = kat()
+    res = query_reads(g1.db, [z["S"].tobytes(), z["amb_seq"].tobytes(), z["low_seq"].tobytes()],
+                      _sk(g1), with_sketches=True)
+    assert np.array_equal(res[0][2][0], z["S_win0"]) and np.array_equal(res[0][2][1], z["S_win1"])
+    assert np.array_equal(res[1][2][0], z["amb_feats"])
+    assert np.array_equal(res[2][2][0], z["low_feats"])
+
+
+def _check(res, exp, reads, k):
+    for i, (allh, top, sks) in enumerate(res):
+        # the GPU enumerates every window; the reference only sketches those with >= k characters
+        a, b = reads[i]
+        kept = [s for s, keep in zip(sks, _window_keeps(a, b, k)) if keep]
+        assert len(kept) == len(exp.sketches[i]), i
+        for x, y in zip(kept, exp.sketches[i]):
+            assert np.array_equal(x, y), i
+        assert np.array_equal(allh, exp.allhits[i]), i
+        assert top == exp.top[i], i
+
+
+def _window_keeps(a, b, k, w=127, stride=112):
+    """for every window the GPU enumerates (mate 1 then mate 2, empty mate 2 not enumerated;
+    an empty mate 1 with a non-empty mate 2 is dropped): True if it has >= k characters"""
+    keeps = []
+    seqs = [a] if len(b) == 0 else ([b] if len(a) == 0 else [a, b])
+    for s in seqs:
+        n = len(s)
+        if n <= w:
+            keeps.append(n >= k)
+            continue
+        full = (n - w) // stride + 1
+        keeps += [True] * full
+        if full * stride < n:
+            keeps.append(n - full * stride >= k)
+    return keeps
+
+
+@pytest.mark.parametrize("tag,maxc,insert", [("c2_", 2, 0), ("c5_", 5, 0), ("c2i_", 2, 1000)])
+def test_g1_matches_reference(g1, tag, maxc, insert):
+    from metacache_b200.database import query_reads
+    res = query_reads(g1.db, g1.reads, _sk(g1), max_candidates=maxc, insert_size_max=insert,
+                      copy_all_hits=True, with_sketches=True, batch_queries=300)
+    assert len(res) == len(g1.reads)
+    _check(res, g1.expected(tag), g1.reads, g1.k)
+
+
+def test_g1_tophits_without_allhits_and_tiny_batches(g1):
+    from metacache_b200.database import query_reads
+    exp = g1.expected("c2_")
+    res = query_reads(g1.db, g1.reads, _sk(g1), copy_all_hits=False, batch_queries=7)
+    assert [r[1] for r in res] == exp.top
+
+
+def test_two_parts_merge_matches_reference_per_part():
+    from metacache_b200.database import Database, query_reads
+    from oracle import mc_oracle as O
+    g1, g2 = G1(), G2()
+    db = Database(0, 2)
+    for p in (0, 1):
+        db.load_part_arrays(p, *g2.parts[p])
+    res = query_reads(db, g1.reads, copy_all_hits=True)
+    e0, e1 = g2.expected(0), g2.expected(1)
+    for i, (allh, top) in enumerate(res):
+        assert np.array_equal(allh, np.concatenate([e0.allhits[i], e1.allhits[i]])), i
+        assert top == O.merge_tops([e0.top[i], e1.top[i]], 2), i
+    db.close()
+
+
+def test_lowest_rank_merge_matches_oracle(g1):
+    """`-lowest` above sequence: candidates of targets sharing a taxon are merged
+    (candidate_generation.hpp:203-228)."""
+    from metacache_b200.database import query_reads
+    from oracle import mc_oracle as O
+    ntgt = len(g1.target_windows)
+    # G0,G0m1,G0m2 share taxon 100, G3* 101, G7* 102, target 5 has no ancestor (dropped)
+    tax = np.arange(1, ntgt + 1, dtype=np.uint64)
+    for base, key in ((0, 100), (3, 101), (7, 102)):
+        tax[base] = key
+    tax[10:12], tax[12:14], tax[14:16], tax[5] = 100, 101, 102, 0
+    g1.db.set_target_taxa(tax)
+    tab = O.Table(g1.keys, g1.sizes, g1.values)
+    try:
+        for maxc in (2, 4):
+            res = query_reads(g1.db, g1.reads, _sk(g1), max_candidates=maxc, copy_all_hits=False)
+            for i, (a, b) in enumerate(g1.reads):
+                _, top = O.query(tab, a, b, maxc=maxc, tax_of_tgt=tax)
+                assert res[i][1] == top, (i, maxc)
+    finally:
+        g1.db.set_target_taxa(None)
+
+
+def test_heavy_paths_give_identical_results(g1):
+    """force reads through the CTA kernel (shared and global-memory variants)"""
+    import ctypes as C
+    from metacache_b200 import _lib
+    from metacache_b200.database import QueryBatch, make_candidate_generation_rules
+    exp = g1.expected("c2_")
+    heavy = [i for i, a in enumerate(exp.allhits) if len(a) > 512]
+    assert len(heavy) >= 5            # the repeat target produces thousands of locations
+    huge = [i for i, a in enumerate(exp.allhits) if len(a) > 16384]
+    assert len(huge) >= 1             # exercises the global-scratch variant
+    qb = QueryBatch(g1.db, 64, 1 << 20, 2, True, 1)
+    hd = qb.host_data(0)
+    for i in heavy[:60]:
+        a, b = g1.reads[i]
+        assert qb.add_paired_read(0, a, b, _sk(g1), make_candidate_generation_rules(len(a), len(b)))
+    g1.db.query_gpu_async(qb, 0, _sk(g1))
+    hd.wait_for_results()
+    for s, i in enumerate(heavy[:60]):
+        assert np.array_equal(hd.allhits(s), exp.allhits[i]), i
+        assert [c.as_tuple() for c in hd.top_candidates(s) if c.hits] == exp.top[i], i
+    qb.close()
+
+
+def test_device_builder_matches_reference_build(g1):
+    """mcb200_db_build_part_from_targets vs the reference `metacache build` of the same FASTA"""
+    import ctypes as C
+    import torch
+    from metacache_b200 import _lib
+    from metacache_b200.database import Database
+    flat = np.concatenate([np.frombuffer(t, np.uint8) for t in g1.targets])
+    off = np.zeros(len(g1.targets) + 1, np.uint64)
+    off[1:] = np.cumsum([len(t) for t in g1.targets])
+    d_bases = torch.from_numpy(flat).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    db = Database(0, 1)
+    sk = _sk(g1).c()
+    wins = np.zeros(len(g1.targets), np.uint32)
+    _lib.check(_lib.lib().mcb200_db_build_part_from_targets(
+        db._h, 0, d_bases.data_ptr(), d_off.data_ptr(), len(g1.targets), 0, C.byref(sk), 254, 0.0,
+        wins.ctypes.data))
+    assert np.array_equal(wins, g1.target_windows)
+    keys, sizes, values = db.export_part(0)
+    assert len(keys) == len(g1.keys) and len(values) == len(g1.values)
+    o = np.argsort(keys)
+    ro = np.argsort(g1.keys)
+    assert np.array_equal(keys[o], g1.keys[ro]) and np.array_equal(sizes[o], g1.sizes[ro])
+    offs = np.zeros(len(sizes) + 1, np.int64); np.cumsum(sizes, out=offs[1:])
+    roffs = np.zeros(len(g1.sizes) + 1, np.int64); np.cumsum(g1.sizes, out=roffs[1:])
+    for a, b in zip(o, ro):
+        assert np.array_equal(values[offs[a]:offs[a + 1]], g1.values[roffs[b]:roffs[b + 1]])
+    db.close()
+
+
+def test_random_reads_against_oracle(g1):
+    """seeded synthetic reads (C2-like recipe at small scale) vs the oracle"""
+    from metacache_b200.database import query_reads
+    from oracle import mc_oracle as O
+    rng = np.random.default_rng(7)
+    tab = O.Table(g1.keys, g1.sizes, g1.values)
+    reads = []
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for _ in range(3000):
+        t = g1.targets[rng.integers(len(g1.targets))]
+        o = int(rng.integers(0, len(t) - 150))
+        a = np.frombuffer(t[o:o + 150], np.uint8).copy()
+        m = rng.random(150) < 0.01
+        a[m] = rng.choice(acgt, int(m.sum()))
+        a[rng.random(150) < 0.001] = ord("N")
+        reads.append(a.tobytes())
+    res = query_reads(g1.db, reads, _sk(g1), copy_all_hits=True, batch_queries=1024)
+    for i, r in enumerate(reads):
+        allh, top = O.query(tab, r, b"")
+        assert np.array_equal(res[i][0], allh), i
+        assert res[i][1] == top, i
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
+                    reason="oracle/_ref/c1 not present (built from /root/reference by build())")
+def test_c1_bundled_database_matches_reference_golden_file():
+    """BASELINE config C1: reference-built `bacteria1` + bundled reads vs classified.expected"""
+    from metacache_b200 import formatting
+    from metacache_b200.database import Database, query_reads
+    from oracle import refio
+    db = Database.read(os.path.join(C1, "bacteria1"))
+    names = db.meta.target_names()
+    expected, section = {}, None
+    for line in open(os.path.join(C1, "classified.expected")):
+        if line.startswith("# data/"):
+            section = line.strip()[7:]
+        if line.startswith("#"):
+            continue
+        cols = line.rstrip("\n").split("\t|\t")
+        if len(cols) == 6 and cols[0].isdigit():
+            expected.setdefault(section, {})[int(cols[0])] = (cols[3], cols[4])   # by query id
+    single = refio.read_fasta(os.path.join(C1, "single.fa"))
+    pf = refio.read_fasta(os.path.join(C1, "pairs.fa"))
+    p1 = refio.read_fasta(os.path.join(C1, "pair.1.fa"))
+    p2 = refio.read_fasta(os.path.join(C1, "pair.2.fa"))
+    runs = {
+        "single": [(s, b"") for _, s in single],
+        "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)],
+        "pair.1 + data/pair.2": [(a[1], b[1]) for a, b in zip(p1, p2)],
+    }
+    total = 0
+    for sec, items in runs.items():
+        exp = expected[sec]
+        res = query_reads(db, items, copy_all_hits=True)
+        for qid, (allh, top) in enumerate(res, start=1):
+            if qid not in exp:
+                continue
+            assert formatting.format_all_hits(allh, names) == exp[qid][0], (sec, qid)
+            want = exp[qid][1] if exp[qid][1] != "--" else ""
+            assert formatting.format_top_hits(top, names) == want, (sec, qid)
+            total += 1
+    assert total > 30000
+    db.close()

@@ -1,0 +1,121 @@
+"""The oracle (oracle/mc_oracle.c) against reference-generated golden vectors. CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mc_oracle as O
+from tests.golden_util import C1, G1, G2, kat
+
+
+def test_kat_hash_and_revcomp():
+    z = kat()
+    for x, y in zip(z["hash_in"], z["hash_out"]):
+        assert O.hash32(int(x)) == int(y)
+    assert O.revcomp32(0x1B, 4) == 27
+    assert O.canonical32(0xFF, 4) == 0
+    assert O.revcomp32(0x12345678, 16) == 0xD26AE37B
+    assert O.canonical32(0x12345678, 16) == 0x12345678
+
+
+def test_kat_sketches():
+    z = kat()
+    sk = O.sketch_sequence(z["S"].tobytes())
+    assert len(sk) == 2
+    assert np.array_equal(sk[0], z["S_win0"]) and np.array_equal(sk[1], z["S_win1"])
+    assert np.array_equal(O.sketch_sequence(z["amb_seq"].tobytes())[0], z["amb_feats"])
+    assert np.array_equal(O.sketch_sequence(z["low_seq"].tobytes())[0], z["low_feats"])
+
+
+@pytest.mark.parametrize("n,expect", [(0, 1), (16, 1), (127, 1), (128, 2), (150, 2), (239, 3), (240, 3),
+                                      (351, 4), (352, 4), (19000, 170)])
+def test_num_windows(n, expect):
+    # hash_dna.hpp:54-75
+    assert O.num_windows(n) == expect
+
+
+@pytest.fixture(scope="module")
+def g1():
+    g = G1()
+    g.table = O.Table(g.keys, g.sizes, g.values)
+    return g
+
+
+@pytest.mark.parametrize("tag,maxc,insert", [("c2_", 2, 0), ("c5_", 5, 0), ("c2i_", 2, 1000)])
+def test_oracle_matches_reference_g1(g1, tag, maxc, insert):
+    exp = g1.expected(tag)
+    assert len(exp.top) == len(g1.reads)
+    for i, (a, b) in enumerate(g1.reads):
+        sk = [x for x in O.sketch_sequence(a, g1.k, g1.s, g1.w, g1.stride) if x is not None]
+        sk += [x for x in O.sketch_sequence(b, g1.k, g1.s, g1.w, g1.stride) if x is not None]
+        assert len(sk) == len(exp.sketches[i]), i
+        for x, y in zip(sk, exp.sketches[i]):
+            assert np.array_equal(x, y), i
+        allh, top = O.query(g1.table, a, b, g1.k, g1.s, g1.w, g1.stride, maxc=maxc, insert_size_max=insert)
+        assert np.array_equal(allh, exp.allhits[i]), i
+        assert top == exp.top[i], i
+
+
+def test_oracle_two_parts_matches_reference_per_part(g1):
+    g2 = G2()
+    tabs = [O.Table(*p) for p in g2.parts]
+    exps = [g2.expected(0), g2.expected(1)]
+    for i, (a, b) in enumerate(g1.reads):
+        tops = []
+        for p in (0, 1):
+            allh, top = O.query(tabs[p], a, b)
+            assert np.array_equal(allh, exps[p].allhits[i]), (i, p)
+            assert top == exps[p].top[i], (i, p)
+            tops.append(top)
+        # intended all-parts semantics == stable part-ordered merge of per-part tops
+        allh, top = O.query(tabs, a, b)
+        assert np.array_equal(allh, np.concatenate([exps[0].allhits[i], exps[1].allhits[i]])), i
+        assert top == O.merge_tops(tops, 2), i
+
+
+def test_candidates_tie_breaks_and_ranges():
+    # candidate_generation.hpp:47-108: first strictly best range wins; stable top-k
+    loc = lambda t, w: (t << 32) | w
+    locs = [loc(1, 5), loc(1, 6), loc(1, 9), loc(1, 10), loc(2, 1), loc(2, 1), loc(3, 7), loc(3, 8)]
+    assert O.candidates(locs, 3, 2) == [(1, 2, 5, 6), (2, 2, 1, 1)]
+    assert O.candidates(locs, 3, 3) == [(1, 2, 5, 6), (2, 2, 1, 1), (3, 2, 7, 8)]
+    assert O.candidates(locs, 6, 1) == [(1, 4, 5, 10)]
+    assert O.candidates([], 3, 2) == []
+    # taxon merge (-lowest above sequence): targets 1 and 3 share a taxon
+    tax = np.asarray([0, 7, 8, 7], np.uint64)
+    assert O.candidates(locs + [loc(3, 8)], 3, 2, tax) == [(3, 3, 7, 8), (2, 2, 1, 1)]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
+                    reason="oracle/_ref/c1 not built (needs /root/reference)")
+def test_oracle_matches_reference_golden_file():
+    """oracle vs the reference's OWN golden test/data/classified.expected (single.fa section)."""
+    from metacache_b200 import dbformat, formatting
+    from oracle import refio
+    meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
+    c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
+    tab = O.Table(c.keys, c.sizes, c.values)
+    names = meta.target_names()
+    reads = refio.read_fasta(os.path.join(C1, "single.fa"))
+    expected = {}
+    section = None
+    for line in open(os.path.join(C1, "classified.expected")):
+        if line.startswith("# data/"):
+            section = line.strip()[7:]
+        if section != "single" or line.startswith("#"):
+            continue
+        cols = line.rstrip("\n").split("\t|\t")
+        if len(cols) == 6:
+            expected[cols[1]] = (cols[3], cols[4])
+    assert len(expected) > 10000
+    checked = 0
+    for hdr, seq in reads:
+        h = hdr.split()[0]
+        if h not in expected:
+            continue
+        allh, top = O.query(tab, seq, b"")
+        assert formatting.format_all_hits(allh, names) == expected[h][0], h
+        want_top = expected[h][1] if expected[h][1] != "--" else ""
+        assert formatting.format_top_hits(top, names) == want_top, h
+        checked += 1
+    assert checked > 10000
