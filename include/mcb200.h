@@ -178,6 +178,9 @@ const uint32_t* mcb200_batch_sketch (const mcb200_batch* b, uint32_t slot, uint3
                                      uint32_t* n);
 /* first window index of query i (num_queries+1 valid entries)                */
 uint32_t mcb200_batch_query_window_offset (const mcb200_batch* b, uint32_t slot, uint32_t query);
+/* device time from the start of slot `first_slot`'s submit to the completion of
+ * the last of n_slots consecutive slots (CUDA events; all must be waited)    */
+int mcb200_batch_span_ms (const mcb200_batch* b, uint32_t first_slot, uint32_t n_slots, float* ms);
 /* device time of the last completed submit on this slot, CUDA events on the
  * slot's stream: total (H2D..D2H) and kernels only; milliseconds             */
 int mcb200_batch_last_timing (const mcb200_batch* b, uint32_t slot, float* total_ms,
@@ -212,6 +215,13 @@ int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
  * d_top[n_queries][max_candidates] (device).                                  */
 int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
                               void* stream);
+/* stage 3+4 for ONE part on sketches computed elsewhere (another GPU's share of
+ * the reads, received through NCCL): d_feats[nwin][sketchlen] padded with
+ * 0xFFFFFFFF, d_qry_win_off[n_queries+1], d_max_win[n_queries].              */
+int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part, const uint32_t* d_feats,
+                                  const uint32_t* d_qry_win_off, const uint32_t* d_max_win,
+                                  uint32_t n_queries, uint32_t sketchlen, mcb200_candidate* d_top,
+                                  void* stream);
 /* stable part-ordered merge of n_lists candidate lists:
  * d_parts[n_lists][n_queries][max_candidates] -> d_out[n_queries][max_candidates]
  * (mode_merge.cpp:158-240 / candidate_generation.hpp:172-231 re-insert).     */
@@ -234,6 +244,15 @@ const uint64_t* mcb200_workspace_allhits_offsets (const mcb200_workspace* ws); /
  * [2] by the global-memory kernel, [3] total locations gathered,
  * [4] total features probed, [5] total table buckets (32 B) read             */
 int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8]);
+/* per-stage device times of the last calls, CUDA events on the caller's stream
+ * (enable first): ms = [encode, window tables, sketch, fused probe+reduce warp
+ * kernel (sum over parts), heavy-read CTA kernel (sum over parts), merge, 0,
+ * number of calls summed]; sums over all calls since the previous stage_times  */
+int mcb200_workspace_set_profiling (mcb200_workspace* ws, int on);
+int mcb200_workspace_stage_times   (mcb200_workspace* ws, float ms[8]);
+/* locations a warp can hold in shared memory in the fused kernel before the
+ * read is handed to the CTA kernel; power of two in [64, 2048], default 512   */
+int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap);
 /* number of kernel launches issued by this library in this process           */
 uint64_t mcb200_kernel_launches (void);
 

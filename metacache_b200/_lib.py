@@ -97,11 +97,13 @@ _SIGS = {
     "mcb200_batch_allhits": (C.POINTER(C.c_uint64), [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "mcb200_batch_sketch": (C.POINTER(C.c_uint32), [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mcb200_batch_query_window_offset": (C.c_uint32, [_P, C.c_uint32, C.c_uint32]),
+    "mcb200_batch_span_ms": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "mcb200_batch_last_timing": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mcb200_workspace_create": (_P, [_P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int]),
     "mcb200_workspace_destroy": (None, [_P]),
     "mcb200_sketch_device": (C.c_int, [_P, C.POINTER(DevQueries), C.POINTER(Sketching), _P]),
     "mcb200_query_part_device": (C.c_int, [_P, C.c_uint32, _P, _P]),
+    "mcb200_query_sketches_device": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_merge_candidates_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_query_device": (C.c_int, [_P, C.POINTER(DevQueries), C.POINTER(Sketching), _P, _P]),
     "mcb200_workspace_num_windows": (C.c_uint32, [_P]),
@@ -110,6 +112,9 @@ _SIGS = {
     "mcb200_workspace_allhits": (_P, [_P]),
     "mcb200_workspace_allhits_offsets": (_P, [_P]),
     "mcb200_workspace_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "mcb200_workspace_set_profiling": (C.c_int, [_P, C.c_int]),
+    "mcb200_workspace_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "mcb200_workspace_set_warp_capacity": (C.c_int, [_P, C.c_uint32]),
     "mcb200_kernel_launches": (C.c_uint64, []),
 }
 

@@ -321,7 +321,37 @@ struct mcb200_workspace {
     uint64_t win_bound = 0;
     bool sketched = false;
     cudaStream_t last_stream = nullptr;
+
+    // optional per-stage CUDA events (mcb200_workspace_set_profiling): one set per call,
+    // summed and recycled by mcb200_workspace_stage_times
+    struct EventSet {
+        cudaEvent_t sk[4] = {nullptr, nullptr, nullptr, nullptr};   // encode | windows | sketch
+        std::vector<cudaEvent_t> q;                                  // 3 per part: warp | heavy
+        cudaEvent_t merge[2] = {nullptr, nullptr};
+        bool sketched = false, merged = false;
+        std::vector<char> part_done;
+    };
+    bool profiling = false;
+    std::vector<EventSet> ev_sets;
+    size_t ev_used = 0;              // sets in use since the last stage_times call
+    EventSet* ev = nullptr;          // set of the call in flight
 };
+
+static int next_event_set (mcb200_workspace* ws) {
+    if (ws->ev_used == ws->ev_sets.size()) {
+        mcb200_workspace::EventSet e;
+        for (auto& x : e.sk) CU(cudaEventCreate(&x));
+        for (auto& x : e.merge) CU(cudaEventCreate(&x));
+        e.q.resize(ws->db->parts.size() * 3, nullptr);
+        for (auto& x : e.q) CU(cudaEventCreate(&x));
+        e.part_done.assign(ws->db->parts.size(), 0);
+        ws->ev_sets.push_back(std::move(e));
+    }
+    ws->ev = &ws->ev_sets[ws->ev_used++];
+    ws->ev->sketched = ws->ev->merged = false;
+    std::fill(ws->ev->part_done.begin(), ws->ev->part_done.end(), 0);
+    return 0;
+}
 
 static int validate_sketching (const mcb200_sketching* sk) {
     if (!sk) return fail(MCB200_EINVAL, "null sketching options");
@@ -372,7 +402,41 @@ extern "C" void mcb200_workspace_destroy (mcb200_workspace* ws) {
     ws->scratch.release(); ws->error.release(); ws->part_tops.release(); ws->hit_counts.release();
     ws->hit_offsets.release(); ws->allhits.release();
     if (ws->scan_tmp) cudaFree(ws->scan_tmp);
+    for (auto& es : ws->ev_sets) {
+        for (auto& e : es.sk) if (e) cudaEventDestroy(e);
+        for (auto& e : es.q) if (e) cudaEventDestroy(e);
+        for (auto& e : es.merge) if (e) cudaEventDestroy(e);
+    }
     delete ws;
+}
+
+extern "C" int mcb200_workspace_set_profiling (mcb200_workspace* ws, int on) {
+    if (!ws) return fail(MCB200_EINVAL, "null argument");
+    ws->profiling = on != 0;
+    ws->ev_used = 0; ws->ev = nullptr;
+    return 0;
+}
+
+extern "C" int mcb200_workspace_stage_times (mcb200_workspace* ws, float ms[8]) {
+    if (!ws || !ms) return fail(MCB200_EINVAL, "null argument");
+    CU(cudaSetDevice(ws->db->device));
+    if (ws->last_stream || ws->ev_used) CU(cudaStreamSynchronize(ws->last_stream));
+    for (int i = 0; i < 8; ++i) ms[i] = 0.f;
+    for (size_t k = 0; k < ws->ev_used; ++k) {
+        auto& es = ws->ev_sets[k];
+        float t = 0.f;
+        if (es.sketched)
+            for (int i = 0; i < 3; ++i) { CU(cudaEventElapsedTime(&t, es.sk[i], es.sk[i + 1])); ms[i] += t; }
+        for (size_t p = 0; p < es.part_done.size(); ++p) {
+            if (!es.part_done[p]) continue;
+            CU(cudaEventElapsedTime(&t, es.q[p * 3], es.q[p * 3 + 1])); ms[3] += t;
+            CU(cudaEventElapsedTime(&t, es.q[p * 3 + 1], es.q[p * 3 + 2])); ms[4] += t;
+        }
+        if (es.merged) { CU(cudaEventElapsedTime(&t, es.merge[0], es.merge[1])); ms[5] += t; }
+    }
+    ms[7] = float(ws->ev_used);       // number of calls summed
+    ws->ev_used = 0; ws->ev = nullptr;
+    return 0;
 }
 
 extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
@@ -400,14 +464,18 @@ extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_quer
     CU(ws->win_seq.ensure(bound));
     CU(ws->feats.ensure(bound * sk->sketchlen));
 
+    if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; CU(cudaEventRecord(ws->ev->sk[0], st)); }
     launch_encode(q->bases, q->n_bases, ws->codes.p, ws->amb.p, st);
+    if (ws->profiling) CU(cudaEventRecord(ws->ev->sk[1], st));
     launch_count_windows(q->seq_offsets, q->n_seqs, ws->sk, ws->seq_nwin.p, st);
     CU(cudaMemsetAsync(ws->seq_nwin.p + q->n_seqs, 0, 4, st));
     device_scan_u32(ws->seq_nwin.p, ws->seq_win_off.p, uint64_t(q->n_seqs) + 1, ws->scan_tmp, ws->scan_tmp_bytes, st);
     launch_fill_windows(ws->seq_win_off.p, q->seq_query, q->n_seqs, q->n_queries, ws->win_seq.p,
                         ws->qry_win_off.p, st);
+    if (ws->profiling) CU(cudaEventRecord(ws->ev->sk[2], st));
     launch_sketch(ws->codes.p, ws->amb.p, q->seq_offsets, ws->seq_win_off.p, ws->win_seq.p,
                   ws->seq_win_off.p + q->n_seqs, ws->sk, ws->feats.p, ws->db->sm_count, st);
+    if (ws->profiling) { CU(cudaEventRecord(ws->ev->sk[3], st)); ws->ev->sketched = true; }
     CU(cudaGetLastError());
     ws->sketched = true;
     return 0;
@@ -445,8 +513,13 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
     if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
     CU(cudaMemsetAsync(ws->heavy_count.p, 0, 8, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
+    if (ws->profiling && !ws->ev) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
+    const bool prof = ws->profiling && ws->ev && ws->ev->q.size() >= (size_t(part) + 1) * 3;
+    if (prof) CU(cudaEventRecord(ws->ev->q[part * 3], st));
     launch_query_warp(a, ws->warp_cap, ws->db->sm_count, st);
+    if (prof) CU(cudaEventRecord(ws->ev->q[part * 3 + 1], st));
     launch_query_heavy(a, ws->db->sm_count, st);
+    if (prof) { CU(cudaEventRecord(ws->ev->q[part * 3 + 2], st)); ws->ev->part_done[part] = 1; }
     CU(cudaGetLastError());
     return 0;
 }
@@ -464,6 +537,39 @@ extern "C" int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mc
     // a read that outgrows the scratch pool raises the sticky device flag 3; callers see it
     // through mcb200_workspace_counters() (device API) or batch_wait (which grows and retries)
     return query_part(ws, part, d_top, nullptr, st);
+}
+
+extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part,
+                                             const uint32_t* d_feats, const uint32_t* d_qry_win_off,
+                                             const uint32_t* d_max_win, uint32_t n_queries,
+                                             uint32_t sketchlen, mcb200_candidate* d_top, void* stream) {
+    if (!ws || !d_feats || !d_qry_win_off || !d_max_win || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (sketchlen < 1 || sketchlen > 32) return fail(MCB200_EINVAL, "sketchlen %u unsupported (1..32)", sketchlen);
+    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished)
+        return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (n_queries > ws->max_queries) return fail(MCB200_EINVAL, "batch exceeds workspace capacity");
+    CU(cudaSetDevice(ws->db->device));
+    if (n_queries == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    if (ws->scratch_entries == 0) { int rc = ensure_scratch(ws, 1ull << 22); if (rc) return rc; }
+    mcb200_dev_queries q{}; q.max_win = d_max_win; q.n_queries = n_queries;
+    const mcb200_dev_queries saved_q = ws->q; const SketchParams saved_sk = ws->sk;
+    ws->q = q; ws->sk.s = sketchlen;
+    QueryArgs a = make_args(ws, part, d_top);
+    ws->q = saved_q; ws->sk = saved_sk;
+    a.feats = d_feats; a.qry_win_off = d_qry_win_off;
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 8, st));
+    CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
+    if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
+    const bool prof = ws->profiling && ws->ev;
+    if (prof) CU(cudaEventRecord(ws->ev->q[part * 3], st));
+    launch_query_warp(a, ws->warp_cap, ws->db->sm_count, st);
+    if (prof) CU(cudaEventRecord(ws->ev->q[part * 3 + 1], st));
+    launch_query_heavy(a, ws->db->sm_count, st);
+    if (prof) { CU(cudaEventRecord(ws->ev->q[part * 3 + 2], st)); ws->ev->part_done[part] = 1; }
+    CU(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int mcb200_merge_candidates_device (mcb200_workspace* ws, const mcb200_candidate* d_parts,
@@ -541,7 +647,9 @@ extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queri
             if (rc) return rc;
         }
         if (np > 1) {
+            if (ws->profiling && ws->ev) CU(cudaEventRecord(ws->ev->merge[0], st));
             launch_merge_candidates(ws->part_tops.p, np, nq, ws->maxc, ws->db->d_tax, ws->db->n_tax, d_top, st);
+            if (ws->profiling && ws->ev) { CU(cudaEventRecord(ws->ev->merge[1], st)); ws->ev->merged = true; }
             CU(cudaGetLastError());
         }
         // The scratch-pool check needs a sync; callers on the fast path check it
@@ -556,6 +664,13 @@ extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queri
         if (rc) return rc;
     }
     return fail(MCB200_ENOMEM, "scratch pool exhausted");
+}
+
+extern "C" int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap) {
+    if (!ws) return fail(MCB200_EINVAL, "null argument");
+    if (cap < 64 || cap > 2048 || (cap & (cap - 1))) return fail(MCB200_EINVAL, "warp capacity must be a power of two in [64, 2048]");
+    ws->warp_cap = cap;
+    return 0;
 }
 
 extern "C" uint32_t mcb200_workspace_num_windows (const mcb200_workspace* ws) {
@@ -996,6 +1111,21 @@ extern "C" uint32_t mcb200_batch_query_window_offset (const mcb200_batch* b, uin
     const Slot_& s = b->slots[slot];
     if (query > s.sub_queries) return s.n_windows;
     return s.h_qry_win_off.p[query];
+}
+
+extern "C" int mcb200_batch_span_ms (const mcb200_batch* b, uint32_t first_slot, uint32_t n_slots, float* ms) {
+    if (!b || !ms || n_slots == 0 || first_slot + n_slots > b->slots.size()) return fail(MCB200_EINVAL, "bad slot range");
+    CU(cudaSetDevice(b->db->device));
+    float best = 0.f;
+    for (uint32_t i = 0; i < n_slots; ++i) {
+        const Slot_& s = b->slots[first_slot + i];
+        if (!s.waited) return fail(MCB200_ESTATE, "slot %u: wait() first", first_slot + i);
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, b->slots[first_slot].ev_start, s.ev_done));
+        best = std::max(best, t);
+    }
+    *ms = best;
+    return 0;
 }
 
 extern "C" int mcb200_batch_last_timing (const mcb200_batch* b, uint32_t slot, float* total_ms,

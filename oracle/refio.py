@@ -73,5 +73,7 @@ def parse_harness_output(path):
 def run_harness(db, reads_txt, out_bin="-", **kw):
     """-> (stdout stats dict).  kw: maxcand, insert, part, threads, repeat, sketches, allhits"""
     cmd = [HARNESS, db, reads_txt, out_bin] + [f"{k}={v}" for k, v in kw.items()]
-    so = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
-    return {k: float(v) for k, v in (kv.split("=") for kv in so.split())}
+    lines = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    out = {k: float(v) for k, v in (kv.split("=") for kv in lines[-1].split())}
+    out["passes"] = [float(l.split("seconds=")[1]) for l in lines[:-1] if l.startswith("pass=")]
+    return out
