@@ -250,8 +250,9 @@ int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8]);
  * number of calls summed]; sums over all calls since the previous stage_times  */
 int mcb200_workspace_set_profiling (mcb200_workspace* ws, int on);
 int mcb200_workspace_stage_times   (mcb200_workspace* ws, float ms[8]);
-/* locations a warp can hold in shared memory in the fused kernel before the
- * read is handed to the CTA kernel; power of two in [64, 2048], default 512   */
+/* slots of the per-warp (tgt,win) aggregation table of the fused kernel; a read
+ * with more than cap/2 DISTINCT locations is handed to the CTA kernel; power of
+ * two in [128, 1024], default 256                                             */
 int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap);
 /* number of kernel launches issued by this library in this process           */
 uint64_t mcb200_kernel_launches (void);

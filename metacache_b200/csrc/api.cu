@@ -303,7 +303,7 @@ struct mcb200_workspace {
     uint32_t max_queries = 0, max_seqs = 0, maxc = 2;
     uint64_t max_bases = 0;
     bool want_allhits = false;
-    uint32_t warp_cap = 512;
+    uint32_t warp_cap = 256;       // slots of the per-warp aggregation table
 
     DevBuf<uint32_t> codes, amb, seq_nwin, seq_win_off, win_seq, qry_win_off, feats;
     DevBuf<uint32_t> heavy_list, heavy_count;
@@ -502,7 +502,7 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
     a.heavy_list = ws->heavy_list.p; a.heavy_count = ws->heavy_count.p;
     a.scratch = ws->scratch.p; a.scratch_entries = ws->scratch_entries;
     a.scratch_cursor = ws->scratch_cursor.p;
-    a.counters = ws->counters.p; a.error = ws->error.p;
+    a.counters = ws->profiling ? ws->counters.p : nullptr; a.error = ws->error.p;
     return a;
 }
 
@@ -668,7 +668,7 @@ extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queri
 
 extern "C" int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap) {
     if (!ws) return fail(MCB200_EINVAL, "null argument");
-    if (cap < 64 || cap > 2048 || (cap & (cap - 1))) return fail(MCB200_EINVAL, "warp capacity must be a power of two in [64, 2048]");
+    if (cap < 128 || cap > 1024 || (cap & (cap - 1))) return fail(MCB200_EINVAL, "warp capacity must be a power of two in [128, 1024]");
     ws->warp_cap = cap;
     return 0;
 }

@@ -8,8 +8,12 @@
 // What the GPU reference does in three kernels + bb_segsort through HBM
 // (gpu_hashmap_operations.cuh:847-942, query_batch.cu:542-633,
 // gpu_result_processing.cuh:325-473) is ONE kernel here: a warp owns a read,
-// gathers its locations into shared memory, sorts them there and reduces them
-// to the top candidates; only 16 B per candidate go back to HBM.
+// probes its features, aggregates the returned locations into a small
+// shared-memory hash table keyed by (tgt,win) (a read's hits are dominated by
+// duplicates of a few locations), sorts only the DISTINCT locations and reduces
+// them to the top candidates; only 16 B per candidate go back to HBM.  Reads
+// with too many distinct locations fall through to a CTA-per-read kernel that
+// sorts the raw list (shared memory, or global scratch for huge reads).
 //
 // Closed form used for the sliding window (equivalent to the reference's
 // two-pointer scan): with the read's locations sorted ascending as u64 keys
@@ -114,37 +118,268 @@ __device__ void sequential_candidates_tax (KeyPtr keys, CntPtr cnt, uint32_t H,
 }
 
 // ---------------------------------------------------------------------------
-// fused warp kernel
+// fused warp kernel: probe -> hash-aggregate -> sort distinct -> candidates
 // ---------------------------------------------------------------------------
-struct WarpSmem {
-    uint64_t* keys;     // [cap]
-    uint32_t* cnt;      // [cap]
-    uint64_t* sdata;    // [32]
-    uint32_t* sbase;    // [33]
-    uint32_t* chosen;   // [kMaxCand]
-};
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint32_t kSeqBucket = 16;        // buckets up to this size are read by their own lane
 
-__host__ __device__ inline size_t warp_smem_bytes (uint32_t cap) {
-    return size_t(cap) * 12 + 32 * 8 + 36 * 4 + kMaxCand * 4;
+// per-warp shared memory for a table of T slots (T power of two >= 128):
+//   hkeys[T] u64 | skeys[T] u64 | hcnt[T] u32 | pcnt[T] u32 | misc
+__host__ __device__ inline size_t warp_smem_bytes (uint32_t T) {
+    return size_t(T) * 24 + 64 * 4;
+}
+
+__device__ __forceinline__ uint32_t loc_hash (uint64_t v) {
+    uint32_t h = uint32_t(v) * 0x9E3779B1u ^ uint32_t(v >> 32) * 0x85EBCA6Bu;
+    return h ^ (h >> 15);
+}
+
+// one location into the aggregation table (distinct counter in *ndist)
+__device__ __forceinline__ void agg_insert (uint64_t* hkeys, uint32_t* hcnt, uint32_t mask,
+                                            uint64_t v, uint32_t* ndist)
+{
+    uint32_t h = loc_hash(v) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(hkeys + h),
+                                                 kEmptyKey, v);
+        if (old == kEmptyKey) { atomicAdd(ndist, 1u); atomicAdd(hcnt + h, 1u); return; }
+        if (old == v) { atomicAdd(hcnt + h, 1u); return; }
+        h = (h + 1) & mask;
+    }
+}
+
+// 32 keys, one per lane, ascending across lanes (register bitonic network)
+__device__ __forceinline__ uint64_t warp_sort32 (uint64_t key) {
+    const uint32_t lane = lane_id();
+    #pragma unroll
+    for (uint32_t k = 2; k <= 32; k <<= 1) {
+        #pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t other = __shfl_xor_sync(kFull, key, j);
+            const bool up = (lane & k) == 0;            // ascending block
+            const bool lower = (lane & j) == 0;         // this lane keeps the smaller one
+            const bool take_min = (up == lower);
+            key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+        }
+    }
+    return key;
+}
+
+// statistics (only when profiling is enabled): one set of REDs per warp, no CTA barrier
+__device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint32_t H,
+                                            uint32_t nfeat, uint32_t sectors)
+{
+    if (!a.counters) return;
+    const uint32_t sec = __reduce_add_sync(kFull, sectors);
+    const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
+    if (lane_id() == 0) {
+        // counters: [0] fused queries [3] locations [4] features [5] sectors
+        unsigned long long* c = a.counters + ((blockIdx.x * kQWarps + (threadIdx.x >> 5)) % kCounterSlots) * 8;
+        if (fused) { atomicAdd(c + 0, 1ull); atomicAdd(c + 3, (unsigned long long)H); }
+        atomicAdd(c + 4, (unsigned long long)nf);
+        atomicAdd(c + 5, (unsigned long long)sec);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fast path (top hits only, rank "sequence", W <= kMaxLookupW): no sort at all.
+//   1. probe the read's features (one table bucket load per lane)
+//   2. stream the buckets' locations (coalesced, all loads of a wave in flight)
+//      into a per-warp hash table keyed by (tgt,win) that counts multiplicity
+//   3. for every distinct location j: hits(j) = sum of the counts of (tgt, win_j-d),
+//      d = 0..W-1, found by W-1 more lookups in the same table
+//   4. k rounds of warp arg-max on (hits desc, key asc), excluding chosen targets
+// This is the reference's sort + two-pointer scan + stable top-k, reordered.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kMaxLookupW = 8;
+constexpr uint32_t kMaxProbe   = 48;
+
+__host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
+    // hkeys[T] u64 | hcnt[T] u32 | list[T/2+32] u16 -> hits[T/2+32] u32 | sdata[32] u64 | sbase[34] u32 | misc[34]
+    return size_t(T) * 12 + (size_t(T) / 2 + 32) * 6 + 32 * 8 + 34 * 4 + 34 * 4;
+}
+
+__device__ __forceinline__ bool agg_insert_bounded (uint64_t* hkeys, uint32_t* hcnt, uint32_t mask, uint64_t v)
+{
+    uint32_t h = loc_hash(v) & mask;
+    #pragma unroll 1
+    for (uint32_t probes = 0; probes < kMaxProbe; ++probes) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(hkeys + h),
+                                                 kEmptyKey, v);
+        if (old == kEmptyKey || old == v) { atomicAdd(hcnt + h, 1u); return true; }
+        h = (h + 1) & mask;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint32_t agg_lookup (const uint64_t* hkeys, const uint32_t* hcnt, uint32_t mask, uint64_t k)
+{
+    uint32_t h = loc_hash(k) & mask;
+    for (;;) {
+        const uint64_t x = hkeys[h];
+        if (x == k) return hcnt[h];
+        if (x == kEmptyKey) return 0;
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(kQWarps * 32)
+query_fast_kernel (QueryArgs a, uint32_t T)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* mine = smem_raw + warp * fast_smem_bytes(T);
+    uint64_t* hkeys = reinterpret_cast<uint64_t*>(mine);
+    uint64_t* sdata = hkeys + T;
+    uint32_t* hcnt  = reinterpret_cast<uint32_t*>(sdata + 32);
+    uint32_t* hits  = hcnt + T;                                   // [T/2+32]
+    uint32_t* sbase = hits + (T / 2 + 32);                        // [34]
+    uint32_t* misc  = sbase + 34;                                 // [0] overflow flag, [1..] chosen
+    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 34);     // [T/2+32]
+    const uint32_t mask = T - 1, dmax = T / 2;
+
+    const uint32_t q = blockIdx.x * kQWarps + warp;
+    if (q >= a.nq) return;
+    const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
+    const uint32_t nslots = (w1 - w0) * a.s;
+    const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+    const uint32_t W = __ldg(a.max_win + q);
+    mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
+    uint32_t sectors = 0, nfeat = 0, H = 0;
+
+    if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
+        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+        warp_stats(a, false, 0, 0, 0);
+        return;
+    }
+    for (uint32_t i = lane; i < T; i += 32) { hkeys[i] = kEmptyKey; hcnt[i] = 0; }
+    if (lane == 0) misc[0] = 0;
+    __syncwarp();
+
+    // ---- probe + aggregate -------------------------------------------------
+    bool ok = true;
+    for (uint32_t c = 0; c < nslots; c += 32) {
+        const uint32_t idx = c + lane;
+        const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
+        uint32_t size = 0; uint64_t data = 0;
+        if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
+        const uint32_t incl = warp_incl_scan(size);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        if (total == 0) continue;
+        H += total;
+        sbase[lane] = incl - size;
+        sdata[lane] = data;
+        if (lane == 31) sbase[32] = total;
+        __syncwarp();
+        // waves of 4 x 32 locations: issue all loads of a wave, then insert
+        for (uint32_t p0 = 0; p0 < total; p0 += 128) {
+            uint64_t v[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = p0 + u * 32 + lane;
+                v[u] = kEmptyKey;
+                if (p < total) {
+                    uint32_t b = 0;
+                    #pragma unroll
+                    for (uint32_t step = 16; step > 0; step >>= 1)
+                        if (sbase[b + step] <= p) b += step;
+                    const uint32_t sb = sbase[b];
+                    const uint64_t d = sdata[b];
+                    v[u] = (sbase[b + 1] - sb == 1) ? d : __ldg(a.table.values + d + (p - sb));
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v[u] != kEmptyKey && !agg_insert_bounded(hkeys, hcnt, mask, v[u])) misc[0] = 1;
+        }
+        __syncwarp();
+        if (*reinterpret_cast<volatile uint32_t*>(misc) != 0) { ok = false; break; }
+    }
+
+    if (ok && H == 0) {
+        if (lane == 0) write_empty(top, 0, a.maxc);
+        warp_stats(a, true, 0, nfeat, sectors);
+        return;
+    }
+    // ---- distinct locations: compact the occupied slots ----------------------
+    uint32_t D = 0;
+    if (ok) {
+        for (uint32_t base = 0; base < T && D <= dmax; base += 32) {
+            const bool o = hkeys[base + lane] != kEmptyKey;
+            const uint32_t occ = __ballot_sync(kFull, o);
+            if (o) list[D + __popc(occ & ((1u << lane) - 1u))] = uint16_t(base + lane);
+            D += __popc(occ);
+        }
+        if (D > dmax) ok = false;
+    }
+    if (!ok) {
+        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+        warp_stats(a, false, 0, nfeat, sectors);
+        return;
+    }
+    __syncwarp();
+    // ---- hits(j) and first window of the range, per distinct location ---------
+    // lane-local best over its entries: (hits desc, key asc)
+    uint32_t best_c = 0; uint64_t best_k = kPadKey;
+    for (uint32_t j = lane; j < D; j += 32) {
+        const uint32_t slot = list[j];
+        const uint64_t k = hkeys[slot];
+        uint32_t c = hcnt[slot];
+        const uint32_t win = uint32_t(k);
+        for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup(hkeys, hcnt, mask, k - d);
+        hits[j] = c;
+        if (c > best_c || (c == best_c && k < best_k)) { best_c = c; best_k = k; }
+    }
+    __syncwarp();
+    // ---- top-k distinct targets ----------------------------------------------
+    uint32_t* chosen = misc + 1;
+    uint32_t c = 0;
+    for (; c < a.maxc; ++c) {
+        if (c > 0) {
+            best_c = 0; best_k = kPadKey;
+            for (uint32_t j = lane; j < D; j += 32) {
+                const uint64_t k = hkeys[list[j]];
+                const uint32_t tgt = uint32_t(k >> 32);
+                bool taken = false;
+                for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
+                const uint32_t cj = hits[j];
+                if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
+            }
+        }
+        const uint32_t wmax = __reduce_max_sync(kFull, best_c);
+        if (wmax == 0) break;
+        const bool cand = (best_c == wmax);
+        const uint32_t wt = __reduce_min_sync(kFull, cand ? uint32_t(best_k >> 32) : 0xFFFFFFFFu);
+        const uint32_t ww = __reduce_min_sync(kFull, (cand && uint32_t(best_k >> 32) == wt) ? uint32_t(best_k) : 0xFFFFFFFFu);
+        if (lane == 0) {
+            // first window of the winning range: smallest present window in (ww-W, ww]
+            const uint64_t ke = (uint64_t(wt) << 32) | ww;
+            uint32_t beg = ww;
+            for (uint32_t d = 1; d < W && d <= ww; ++d)
+                if (agg_lookup(hkeys, hcnt, mask, ke - d)) beg = ww - d;
+            top[c] = mcb200_candidate{wt, wmax, beg, ww};
+            chosen[c] = wt;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) write_empty(top, c, a.maxc);
+    warp_stats(a, true, H, nfeat, sectors);
 }
 
 template <bool kTax>
 __global__ void __launch_bounds__(kQWarps * 32)
-query_warp_kernel (QueryArgs a, uint32_t cap)
+query_warp_kernel (QueryArgs a, uint32_t T)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ unsigned long long s_counters[4];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    if (threadIdx.x < 4) s_counters[threadIdx.x] = 0;
-    __syncthreads();
 
-    uint8_t* mine = smem_raw + warp * warp_smem_bytes(cap);
-    WarpSmem sm;
-    sm.keys   = reinterpret_cast<uint64_t*>(mine);
-    sm.sdata  = sm.keys + cap;
-    sm.cnt    = reinterpret_cast<uint32_t*>(sm.sdata + 32);
-    sm.sbase  = sm.cnt + cap;
-    sm.chosen = sm.sbase + 36;
+    uint8_t* mine = smem_raw + warp * warp_smem_bytes(T);
+    uint64_t* hkeys = reinterpret_cast<uint64_t*>(mine);
+    uint64_t* skeys = hkeys + T;
+    uint32_t* hcnt  = reinterpret_cast<uint32_t*>(skeys + T);
+    uint32_t* pcnt  = hcnt + T;                   // prefix sums, later hits(j)
+    uint32_t* misc  = pcnt + T;                   // [0] distinct counter, [1..] chosen targets
+    const uint32_t mask = T - 1, dmax = T / 2;
 
     const uint32_t q = blockIdx.x * kQWarps + warp;
     uint32_t sectors = 0, nfeat = 0, H = 0;
@@ -156,100 +391,180 @@ query_warp_kernel (QueryArgs a, uint32_t cap)
         mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
         bool overflow = false;
 
-        // ---- probe + gather ------------------------------------------------
-        for (uint32_t c = 0; c < nslots; c += 32) {
+        for (uint32_t i = lane; i < T; i += 32) { hkeys[i] = kEmptyKey; hcnt[i] = 0; }
+        if (lane == 0) misc[0] = 0;
+        __syncwarp();
+
+        // ---- probe + aggregate ---------------------------------------------
+        for (uint32_t c = 0; c < nslots && !overflow; c += 32) {
             const uint32_t idx = c + lane;
             const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
             uint32_t size = 0; uint64_t data = 0;
             if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
-            const uint32_t incl = warp_incl_scan(size);
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            if (total == 0) continue;
-            if (H + total > cap) { overflow = true; break; }
-            sm.sbase[lane] = H + incl - size;
-            sm.sdata[lane] = data;
-            if (lane == 31) sm.sbase[32] = H + total;
-            __syncwarp();
-            for (uint32_t p = H + lane; p < H + total; p += 32) {
-                // last b with sbase[b] <= p
-                uint32_t b = 0;
-                #pragma unroll
-                for (uint32_t step = 16; step > 0; step >>= 1)
-                    if (sm.sbase[b + step] <= p) b += step;
-                const uint32_t sb = sm.sbase[b];
-                const uint32_t sz = sm.sbase[b + 1] - sb;
-                const uint64_t d = sm.sdata[b];
-                sm.keys[p] = (sz == 1) ? d : __ldg(a.table.values + d + (p - sb));
+            H += size;
+            if (__any_sync(kFull, size != 0) == 0) continue;
+            // small buckets: every lane walks its own bucket (values are consecutive)
+            const uint32_t own = (size <= kSeqBucket) ? size : 0u;
+            const uint32_t rounds = __reduce_max_sync(kFull, own);
+            for (uint32_t r = 0; r < rounds; ++r) {
+                if (*reinterpret_cast<volatile uint32_t*>(misc) > dmax) { overflow = true; break; }
+                if (r < own) {
+                    const uint64_t v = (size == 1) ? data : a.table.values[data + r];
+                    agg_insert(hkeys, hcnt, mask, v, misc);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            H += total;
+            // large buckets: the whole warp strides over one bucket at a time
+            uint32_t big = __ballot_sync(kFull, size > kSeqBucket);
+            while (big && !overflow) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t bsz = __shfl_sync(kFull, size, src);
+                const uint64_t bof = __shfl_sync(kFull, data, src);
+                for (uint32_t i = 0; i < bsz; i += 32) {
+                    if (*reinterpret_cast<volatile uint32_t*>(misc) > dmax) { overflow = true; break; }
+                    if (i + lane < bsz) agg_insert(hkeys, hcnt, mask, __ldg(a.table.values + bof + i + lane), misc);
+                    __syncwarp();
+                }
+            }
         }
-
-        if (overflow) {
+        H = __reduce_add_sync(kFull, H);
+        __syncwarp();
+        const uint32_t D = misc[0];
+        if (overflow || D > dmax) {
             if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
-        } else if (H == 0) {
+        } else if (D == 0) {
             fused = true;
             if (lane == 0) write_empty(top, 0, a.maxc);
         } else {
             fused = true;
-            // ---- bitonic sort in shared memory ------------------------------
-            const uint32_t n = max(pow2_ceil(H), 2u);
-            for (uint32_t i = H + lane; i < n; i += 32) sm.keys[i] = kPadKey;
-            __syncwarp();
-            for (uint32_t k = 2; k <= n; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = lane; i < (n >> 1); i += 32) {
-                        const uint32_t x = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                        const uint32_t y = x | j;
-                        const uint64_t ka = sm.keys[x], kb = sm.keys[y];
-                        const bool up = (x & k) == 0;
-                        if ((ka > kb) == up) { sm.keys[x] = kb; sm.keys[y] = ka; }
+            // ---- distinct locations, sorted -----------------------------------
+            uint32_t n;
+            if (D <= 32) {
+                // compact through the warp: each lane finds the (lane)-th occupied slot
+                uint32_t got = 0; uint64_t mykey = kPadKey;
+                for (uint32_t base = 0; base < T; base += 32) {
+                    const uint64_t k = hkeys[base + lane];
+                    const uint32_t occ = __ballot_sync(kFull, k != kEmptyKey);
+                    // occupied slot with rank (lane - got) in this round belongs to this lane
+                    const uint32_t want = lane - got;
+                    if (lane >= got && want < uint32_t(__popc(occ))) {
+                        const int src = __fns(occ, 0, want + 1);
+                        mykey = hkeys[base + src];
                     }
-                    __syncwarp();
+                    got += __popc(occ);
+                    if (got >= D) break;
+                }
+                mykey = warp_sort32(mykey);
+                skeys[lane] = mykey;
+                n = 32;
+            } else {
+                uint32_t got = 0;
+                for (uint32_t base = 0; base < T; base += 32) {
+                    const uint64_t k = hkeys[base + lane];
+                    const bool o = (k != kEmptyKey);
+                    const uint32_t occ = __ballot_sync(kFull, o);
+                    if (o) skeys[got + __popc(occ & ((1u << lane) - 1u))] = k;
+                    got += __popc(occ);
+                }
+                n = pow2_ceil(D);
+                for (uint32_t i = D + lane; i < n; i += 32) skeys[i] = kPadKey;
+                __syncwarp();
+                for (uint32_t k = 2; k <= n; k <<= 1) {
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        for (uint32_t i = lane; i < (n >> 1); i += 32) {
+                            const uint32_t x = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                            const uint32_t y = x | j;
+                            const uint64_t ka = skeys[x], kb = skeys[y];
+                            const bool up = (x & k) == 0;
+                            if ((ka > kb) == up) { skeys[x] = kb; skeys[y] = ka; }
+                        }
+                        __syncwarp();
+                    }
                 }
             }
+            __syncwarp();
+            // ---- multiplicities in sorted order -> inclusive prefix sums ---------
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < D; base += 32) {
+                const uint32_t j = base + lane;
+                uint32_t c = 0;
+                if (j < D) {
+                    const uint64_t k = skeys[j];
+                    uint32_t h = loc_hash(k) & mask;
+                    while (hkeys[h] != k) h = (h + 1) & mask;
+                    c = hcnt[h];
+                }
+                const uint32_t incl = warp_incl_scan(c) + carry;
+                if (j < D) pcnt[j] = incl;
+                carry = __shfl_sync(kFull, incl, 31);
+            }
+            __syncwarp();
             if (a.allhits) {
                 uint64_t* dst = a.allhits + a.allhits_off[q];
-                for (uint32_t i = lane; i < H; i += 32) dst[i] = sm.keys[i];
-            }
-            // ---- hits(j) for every entry ---------------------------------------
-            const uint32_t W = __ldg(a.max_win + q);
-            uint32_t best_c = 0, best_j = 0xFFFFFFFFu;
-            for (uint32_t j = lane; j < H; j += 32) {
-                uint32_t c = 1;
-                if (W > 0) {
-                    const uint64_t K = window_floor_key(sm.keys[j], W);
-                    c = j - lower_bound_u64(sm.keys, j, K) + 1;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t e = pcnt[j], b = j ? pcnt[j - 1] : 0u;
+                    const uint64_t k = skeys[j];
+                    for (uint32_t i = b; i < e; ++i) dst[i] = k;
                 }
-                sm.cnt[j] = c;
+            }
+            // ---- hits(j) = locations of the same target inside the window range ----
+            const uint32_t W = __ldg(a.max_win + q);
+            uint32_t* hits = hcnt;                    // table counts are no longer needed
+            __syncwarp();
+            uint32_t best_c = 0, best_j = 0xFFFFFFFFu;
+            for (uint32_t j = lane; j < D; j += 32) {
+                uint32_t f = j;
+                if (W > 1) f = lower_bound_u64(skeys, j, window_floor_key(skeys[j], W));
+                uint32_t c = pcnt[j] - (f ? pcnt[f - 1] : 0u);
+                if (W == 0) c = 1;      // degenerate rule: the scan never widens (candidate_generation.hpp:76-82)
+                hits[j] = c;
                 if (c > best_c) { best_c = c; best_j = j; }
             }
             __syncwarp();
             if (kTax) {
-                if (lane == 0)
-                    sequential_candidates_tax(sm.keys, sm.cnt, H, a.tax_of_tgt, a.n_tax, top, a.maxc);
+                if (lane == 0) {
+                    // sequential insert() with taxon merging over the per-target candidates
+                    mcb200_candidate tl[kMaxCand]; uint64_t tt[kMaxCand]; uint32_t nt = 0;
+                    uint32_t j = 0;
+                    while (j < D) {
+                        const uint32_t tgt = uint32_t(skeys[j] >> 32);
+                        uint32_t bc = 0, bj = j, e = j;
+                        for (; e < D && uint32_t(skeys[e] >> 32) == tgt; ++e)
+                            if (hits[e] > bc) { bc = hits[e]; bj = e; }
+                        uint32_t f = bj;
+                        if (W > 1) f = lower_bound_u64(skeys, bj, window_floor_key(skeys[bj], W));
+                        const mcb200_candidate cand{tgt, bc, uint32_t(skeys[f]), uint32_t(skeys[bj])};
+                        const uint64_t tax = (tgt < a.n_tax) ? a.tax_of_tgt[tgt] : 0ull;
+                        insert_candidate(tl, tt, nt, a.maxc, cand, tax, true);
+                        j = e;
+                    }
+                    for (uint32_t c = 0; c < nt; ++c) top[c] = tl[c];
+                    write_empty(top, nt, a.maxc);
+                }
             } else {
-                // ---- top-k distinct targets ----------------------------------
+                uint32_t* chosen = misc + 1;
                 uint32_t c = 0;
                 for (; c < a.maxc; ++c) {
                     if (c > 0) {
                         best_c = 0; best_j = 0xFFFFFFFFu;
-                        for (uint32_t j = lane; j < H; j += 32) {
-                            const uint32_t tgt = uint32_t(sm.keys[j] >> 32);
+                        for (uint32_t j = lane; j < D; j += 32) {
+                            const uint32_t tgt = uint32_t(skeys[j] >> 32);
                             bool taken = false;
-                            for (uint32_t i = 0; i < c; ++i) taken |= (sm.chosen[i] == tgt);
-                            const uint32_t cj = sm.cnt[j];
+                            for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
+                            const uint32_t cj = hits[j];
                             if (!taken && cj > best_c) { best_c = cj; best_j = j; }
                         }
                     }
                     const uint32_t wmax = __reduce_max_sync(kFull, best_c);
                     if (wmax == 0) break;
                     const uint32_t wj = __reduce_min_sync(kFull, best_c == wmax ? best_j : 0xFFFFFFFFu);
-                    const uint64_t ke = sm.keys[wj];
+                    const uint64_t ke = skeys[wj];
                     if (lane == 0) {
-                        top[c] = mcb200_candidate{uint32_t(ke >> 32), wmax,
-                                                  uint32_t(sm.keys[wj - wmax + 1]), uint32_t(ke)};
-                        sm.chosen[c] = uint32_t(ke >> 32);
+                        uint32_t f = wj;
+                        if (W > 1) f = lower_bound_u64(skeys, wj, window_floor_key(ke, W));
+                        top[c] = mcb200_candidate{uint32_t(ke >> 32), wmax, uint32_t(skeys[f]), uint32_t(ke)};
+                        chosen[c] = uint32_t(ke >> 32);
                     }
                     __syncwarp();
                 }
@@ -257,38 +572,28 @@ query_warp_kernel (QueryArgs a, uint32_t cap)
             }
         }
     }
-    // ---- statistics ---------------------------------------------------------
-    if (a.counters) {
-        const uint32_t sec = __reduce_add_sync(kFull, sectors);
-        const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
-        if (lane == 0) {
-            if (fused) atomicAdd(&s_counters[0], 1ull);
-            if (fused) atomicAdd(&s_counters[1], (unsigned long long)H);
-            atomicAdd(&s_counters[2], (unsigned long long)nf);
-            atomicAdd(&s_counters[3], (unsigned long long)sec);
-        }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            // counters: [0] fused queries [3] locations [4] features [5] sectors
-            const int dst = threadIdx.x == 0 ? 0 : 2 + threadIdx.x;
-            atomicAdd(a.counters + (blockIdx.x % kCounterSlots) * 8 + dst, s_counters[threadIdx.x]);
-        }
-    }
+    warp_stats(a, fused, H, nfeat, sectors);
 }
 
-void launch_query_warp (const QueryArgs& a, uint32_t cap, int, cudaStream_t st)
+void launch_query_warp (const QueryArgs& a, uint32_t T, int, cudaStream_t st)
 {
     if (!a.nq) return;
-    const size_t smem = warp_smem_bytes(cap) * kQWarps;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
-    if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, cap);
-    else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, cap);
+    if (!a.tax_of_tgt && !a.allhits) {
+        // top hits only at rank "sequence": the sort-free kernel
+        query_fast_kernel<<<grid, kQWarps * 32, fast_smem_bytes(T) * kQWarps, st>>>(a, T);
+    } else {
+        const size_t smem = warp_smem_bytes(T) * kQWarps;
+        if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T);
+        else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, T);
+    }
     count_launch();
 }
 

@@ -248,16 +248,43 @@ sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ 
                         if (q + j < nk && ambig == 0) v[j] = hash32(canonical32(kmer, p.k));
                     }
                 }
-                // s smallest unique values of {v[0..3] of all lanes} U {run of all lanes}
                 uint32_t newrun = kNoFeature;
-                for (uint32_t r = 0; r < s_eff; ++r) {
-                    const uint32_t m = min(min(min(v[0], v[1]), min(v[2], v[3])), run);
-                    const uint32_t wm = __reduce_min_sync(kFull, m);
-                    if (wm == kNoFeature) break;
-                    if (lane == r) newrun = wm;
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = (v[j] == wm) ? kNoFeature : v[j];
-                    run = (run == wm) ? kNoFeature : run;
+                if (nk <= 128) {
+                    // single chunk (the default geometry): keep the lane's 4 hashes sorted so the
+                    // lane minimum is v[0] and "remove the selected value" is a shift
+                    #define MCB_CE(a, b) { const uint32_t lo_ = min(v[a], v[b]); v[b] = max(v[a], v[b]); v[a] = lo_; }
+                    MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
+                    // duplicates inside the lane (tandem repeats): keep one, re-sort
+                    if (__any_sync(kFull, (v[0] == v[1] && v[1] != kNoFeature) || (v[1] == v[2] && v[2] != kNoFeature) || (v[2] == v[3] && v[3] != kNoFeature))) {
+                        const bool d1 = v[1] == v[0], d2 = v[2] == v[1], d3 = v[3] == v[2];
+                        if (d1) v[1] = kNoFeature;
+                        if (d2) v[2] = kNoFeature;
+                        if (d3) v[3] = kNoFeature;
+                        MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
+                    }
+                    #undef MCB_CE
+                    #pragma unroll 4
+                    for (uint32_t r = 0; r < s_eff; ++r) {
+                        const uint32_t wm = __reduce_min_sync(kFull, v[0]);
+                        if (wm == kNoFeature) break;
+                        newrun = (lane == r) ? wm : newrun;
+                        const bool hit = (v[0] == wm);
+                        v[0] = hit ? v[1] : v[0];
+                        v[1] = hit ? v[2] : v[1];
+                        v[2] = hit ? v[3] : v[2];
+                        v[3] = hit ? kNoFeature : v[3];
+                    }
+                } else {
+                    // s smallest unique values of {v[0..3] of all lanes} U {run of all lanes}
+                    for (uint32_t r = 0; r < s_eff; ++r) {
+                        const uint32_t m = min(min(min(v[0], v[1]), min(v[2], v[3])), run);
+                        const uint32_t wm = __reduce_min_sync(kFull, m);
+                        if (wm == kNoFeature) break;
+                        if (lane == r) newrun = wm;
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = (v[j] == wm) ? kNoFeature : v[j];
+                        run = (run == wm) ? kNoFeature : run;
+                    }
                 }
                 run = newrun;
             }
@@ -284,7 +311,7 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
         cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const int grid = sm_count * 4;
+    const int grid = sm_count * 8;
     sketch_kernel<<<grid, kSketchThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
                                                       d_nwin, p, feats, tile_windows, stage_bases);
     count_launch();

@@ -234,3 +234,62 @@ def test_c1_bundled_database_matches_reference_golden_file():
             total += 1
     assert total > 30000
     db.close()
+
+
+@pytest.mark.parametrize("maxc", [1, 2, 5])
+def test_fast_kernel_tophits_only_matches_reference(g1, maxc):
+    """top hits without all-hits run through the sort-free kernel (query_fast_kernel)"""
+    from metacache_b200.database import query_reads
+    from oracle import mc_oracle as O
+    res = query_reads(g1.db, g1.reads, _sk(g1), max_candidates=maxc, copy_all_hits=False, batch_queries=500)
+    if maxc in (2, 5):
+        exp = g1.expected("c2_" if maxc == 2 else "c5_")
+        assert [r[1] for r in res] == exp.top
+    else:
+        tab = O.Table(g1.keys, g1.sizes, g1.values)
+        for i, (a, b) in enumerate(g1.reads):
+            assert res[i][1] == O.query(tab, a, b, maxc=1)[1], i
+
+
+def test_fast_kernel_small_table_overflows_to_cta_kernel(g1):
+    """a 128-slot aggregation table sends more reads through the CTA kernel; results identical"""
+    import ctypes as C
+    from metacache_b200 import _lib
+    from metacache_b200.database import QueryBatch, make_candidate_generation_rules
+    exp = g1.expected("c2_")
+    L = _lib.lib()
+    import torch
+    reads = g1.reads
+    flat = np.concatenate([np.frombuffer(a + b, np.uint8) for a, b in reads] + [np.zeros(64, np.uint8)])
+    seq_off, seq_qry, max_win = [0], [], []
+    for i, (a, b) in enumerate(reads):
+        for s in ((a, b) if len(b) and len(a) else ((a,) if len(a) or not len(b) else (b,))):
+            seq_off.append(seq_off[-1] + len(s)); seq_qry.append(i)
+        max_win.append(2 + (len(a) + len(b)) // 112)
+    # note: concatenation order must match: rebuild flat in the same order
+    chunks = []
+    for a, b in reads:
+        for s in ((a, b) if len(b) and len(a) else ((a,) if len(a) or not len(b) else (b,))):
+            chunks.append(np.frombuffer(s, np.uint8))
+    flat = np.concatenate(chunks + [np.zeros(64, np.uint8)])
+    dev = torch.device("cuda", 0)
+    t_b = torch.from_numpy(flat).to(dev)
+    t_o = torch.tensor(seq_off, dtype=torch.int32, device=dev)
+    t_q = torch.tensor(seq_qry, dtype=torch.int32, device=dev)
+    t_w = torch.tensor(max_win, dtype=torch.int32, device=dev)
+    nq, ns, nb = len(reads), len(seq_qry), seq_off[-1]
+    ws = _lib.check_ptr(L.mcb200_workspace_create(g1.db._h, nq, ns, nb + 64, 2, 0))
+    _lib.check(L.mcb200_workspace_set_warp_capacity(ws, 128))
+    _lib.check(L.mcb200_workspace_set_profiling(ws, 1))
+    q = _lib.DevQueries(t_b.data_ptr(), t_o.data_ptr(), t_q.data_ptr(), t_w.data_ptr(), ns, nq, nb)
+    sk = _sk(g1).c()
+    top = torch.empty((nq, 2, 4), dtype=torch.int32, device=dev)
+    _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top.data_ptr(), None))
+    cnt = (C.c_uint64 * 8)()
+    _lib.check(L.mcb200_workspace_counters(ws, cnt))
+    assert cnt[0] + cnt[1] + cnt[2] == nq and cnt[1] > 0 and cnt[2] > 0
+    got = top.cpu().numpy().astype(np.uint32)
+    for i in range(nq):
+        tl = [tuple(int(x) for x in row) for row in got[i] if row[1] > 0]
+        assert tl == exp.top[i], i
+    L.mcb200_workspace_destroy(ws)
