@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--slot-reads", type=int, default=1_000_000, help="reads per host batch slot (e2e)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
+    ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default)")
     ap.add_argument("--cache", default=os.environ.get(
         "MCB200_BENCH_CACHE", "/dev/shm/mcb200_bench" if os.path.isdir("/dev/shm") else "/tmp/mcb200_bench"))
     return ap.parse_args()
@@ -126,8 +128,8 @@ def build_part(args, part, device):
     sk = Sketching(**SK)
     wins = np.zeros(args.targets, np.uint32)
     _lib.check(_lib.lib().mcb200_db_build_part_from_targets(
-        db._h, 0, bases.data_ptr(), off.data_ptr(), args.targets, part * args.targets, C.byref(sk), 254, 0.0,
-        wins.ctypes.data))
+        db._h, 0, bases.data_ptr(), off.data_ptr(), args.targets, part * args.targets, C.byref(sk), 254,
+        args.load_factor, wins.ctypes.data))
     torch.cuda.synchronize(device)
     info = dict(build_s=round(time.time() - t0, 2), keys=db.key_count(0), locations=db.value_count(0),
                 table_gb=round(db.device_bytes(0) / 1e9, 2))
@@ -267,6 +269,8 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
     nq_total = nq * world
     ws = _lib.check_ptr(L.mcb200_workspace_create(db._h, nq, nq, n_bases + 64, MAXC, 0))
+    if args.table_slots:
+        _lib.check(L.mcb200_workspace_set_warp_capacity(ws, args.table_slots))
     q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), nq, nq, n_bases)
     d_top = torch.empty((nq, MAXC, 4), dtype=torch.int32, device=device)
 
@@ -274,31 +278,13 @@ def main():
         def step():
             _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), d_top.data_ptr(), sp))
     else:
-        nwin = 2 * nq     # 150 bp reads: two windows each (checked below)
-        S = SK["sketchlen"]
-        feats_all = torch.empty((world, nwin * S), dtype=torch.int32, device=device)
-        qwo_all = torch.empty((world, nq + 1), dtype=torch.int32, device=device)
-        send = torch.empty((world, nq, MAXC, 4), dtype=torch.int32, device=device)
-        recv = torch.empty((world, nq, MAXC, 4), dtype=torch.int32, device=device)
+        from metacache_b200.distributed import ShardedQuery
+        nwin = sum(1 for _ in range(2)) * nq     # 150 bp reads: two windows each
+        sq = ShardedQuery(db, ws, nq, nwin, SK["sketchlen"], MAXC, device, stream)
+        d_top = sq.top
 
         def step():
-            # 1. sketch my slice of the reads; 2. all-gather the sketches over NVLink
-            _lib.check(L.mcb200_sketch_device(ws, C.byref(q), C.byref(sk), sp))
-            fp = L.mcb200_workspace_sketches(ws)
-            wp = L.mcb200_workspace_query_windows(ws)
-            mine_f = _as_tensor(fp, nwin * S, device)
-            mine_w = _as_tensor(wp, nq + 1, device)
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(feats_all, mine_f)
-                dist.all_gather_into_tensor(qwo_all, mine_w)
-            # 3. probe every rank's reads against my part
-            for j in range(world):
-                _lib.check(L.mcb200_query_sketches_device(ws, 0, feats_all[j].data_ptr(), qwo_all[j].data_ptr(),
-                                                          max_win.data_ptr(), nq, S, send[j].data_ptr(), sp))
-            # 4. exchange partial top hits (slice j goes to rank j) and merge in part order
-            with torch.cuda.stream(stream):
-                dist.all_to_all_single(recv, send)
-            _lib.check(L.mcb200_merge_candidates_device(ws, recv.data_ptr(), world, nq, d_top.data_ptr(), sp))
+            sq.step(q, sk, max_win)
 
     def barrier():
         if dist is not None:
@@ -474,17 +460,6 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
-
-
-def _as_tensor(ptr, n, device):
-    """int32 torch view of `n` u32 at device pointer `ptr` (library-owned memory)"""
-    import torch
-
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
-    return torch.as_tensor(h, device=device)
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -116,6 +117,14 @@ extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
     if (prop.major < 10) {
         fail(MCB200_ENODEVICE, "device %d is sm_%d%d; libmcb200 is built for sm_100a only", device, prop.major, prop.minor);
         delete db; return nullptr;
+    }
+    // random 32-byte bucket probes: ask L2 not to over-fetch neighbouring sectors from HBM
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("MCB200_L2_FETCH")) gran = size_t(atoi(e));
+        if (gran == 32 || gran == 64 || gran == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
+        }
     }
     CUP(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     CUP(cudaMalloc(&db->d_error, sizeof(int)));

@@ -1,0 +1,322 @@
+/******************************************************************************
+ * mcb200_shim.hpp - C++ mirror of the reference's GPU seam over the C ABI.
+ *
+ * Under -DGPU_MODE the reference selects (database.hpp:183-189)
+ *     using feature_store  = gpu_hashmap<feature, location>;
+ *     using result_handler = query_batch<location>;
+ * This header provides those two class templates with the members the rest of
+ * the reference tree calls on the QUERY path, same names
+ * and argument meaning, implemented by libmcb200.so (include/mcb200.h).  Build
+ * members exist and throw: building databases is out of scope of this library
+ * (it consumes `.cache` files written by the reference's `metacache build`).
+ *
+ * Differences a maintainer has to know:
+ *   - `location` is read/written as the same 8 bytes {u32 win, u32 tgt}.
+ *   - `match_candidate::tax` is filled on the host from `target_lineages`
+ *     handed to copy_target_lineages_to_gpus (index = rank, as in the reference).
+ *   - errors are C++ exceptions (std::runtime_error) instead of CUERR/exit(1).
+ *   - one store lives on ONE device (one process per GPU); multi-GPU runs shard
+ *     parts over processes and merge candidates (mcb200_merge_candidates_device).
+ ******************************************************************************/
+#ifndef MCB200_SHIM_HPP
+#define MCB200_SHIM_HPP
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <istream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mcb200.h"
+
+namespace mcb200 {
+
+using part_id   = std::uint32_t;        // config.hpp
+using target_id = std::uint32_t;
+using window_id = std::uint32_t;
+using feature   = std::uint32_t;
+
+/** database.hpp:136-166 */
+struct location {
+    window_id win;
+    target_id tgt;
+    friend bool operator == (const location& a, const location& b) noexcept { return a.tgt == b.tgt && a.win == b.win; }
+    friend bool operator <  (const location& a, const location& b) noexcept {
+        return a.tgt < b.tgt || (a.tgt == b.tgt && a.win < b.win);
+    }
+};
+static_assert(sizeof(location) == 8, "location must match the on-disk layout");
+
+/** hash_dna.hpp:99-163 */
+struct sketching_opt {
+    std::uint8_t  kmerlen   = 16;
+    std::uint32_t sketchlen = 16;
+    std::uint32_t winlen    = 127;
+    std::uint32_t winstride = 112;
+};
+
+/** candidate_structs.hpp:42-104 */
+struct window_range { window_id beg = 0, end = 0; };
+struct match_candidate {
+    const void*   tax;      // const taxon* in the reference
+    target_id     tgt;
+    std::uint32_t hits;
+    window_range  pos;
+};
+static_assert(sizeof(match_candidate) == 24, "match_candidate must be 24 bytes like the reference's");
+
+/** candidate_structs.hpp:110-125 */
+struct candidate_generation_rules {
+    window_id   maxWindowsInRange = 3;
+    std::size_t maxCandidates     = 2;
+    int         mergeBelow        = 0;     // taxon_rank::Sequence
+};
+
+/** span.hpp */
+template <class T> struct span {
+    const T* ptr = nullptr; std::size_t n = 0;
+    const T* begin () const noexcept { return ptr; }
+    const T* end ()   const noexcept { return ptr + n; }
+    std::size_t size () const noexcept { return n; }
+    bool empty () const noexcept { return n == 0; }
+    const T& operator [] (std::size_t i) const noexcept { return ptr[i]; }
+};
+
+[[noreturn]] inline void throw_last (const char* what) {
+    throw std::runtime_error(std::string(what) + ": " + mcb200_last_error());
+}
+
+template <class Location> class query_batch;
+
+//-----------------------------------------------------------------------------
+/** gpu_hashmap<Key,ValueT> (gpu_hashmap.cuh:42-351), query half */
+template <class Key = feature, class ValueT = location>
+class gpu_hashmap
+{
+public:
+    using key_type           = Key;
+    using value_type         = ValueT;
+    using bucket_size_type   = std::uint8_t;
+    using feature_count_type = std::uint64_t;
+    using taxon_rank         = int;
+    /** taxonomy::ranked_lineage reduced to opaque pointers, index = rank (taxonomy.hpp:368) */
+    using ranked_lineage     = std::array<const void*, 21>;
+
+    explicit gpu_hashmap (int device = 0) : device_(device) {}
+    gpu_hashmap (const gpu_hashmap&) = delete;
+    ~gpu_hashmap () { if (db_) mcb200_db_close(db_); if (current() == this) current() = nullptr; }
+
+    /** the store queries are bound to when a query_batch is created without one */
+    static gpu_hashmap*& current () { static gpu_hashmap* c = nullptr; return c; }
+
+    //--- query tables (gpu_hashmap.cu:1320-1362) ---
+    void prepare_query_tables (part_id numParts, unsigned /*replication*/ = 1) {
+        if (db_) mcb200_db_close(db_);
+        db_ = mcb200_db_open(device_, numParts);
+        if (!db_) throw_last("prepare_query_tables");
+        current() = this;
+    }
+    unsigned table_count () const noexcept { return db_ ? mcb200_db_part_count(db_) : 0; }
+    void enable_peer_access () {}     // one process per GPU: no peer chain (gpu_hashmap.cu:1403-1420)
+
+    /** read_binary(istream&, store&, part_id, progress) (gpu_hashmap.cu:813-912):
+     *  the `.cache` stream positioned at its start */
+    friend void read_binary (std::istream& is, gpu_hashmap& m, part_id partId) {
+        std::uint64_t hdr[3];
+        is.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+        if (!is) throw std::runtime_error("could not read database part header");
+        const std::uint64_t nkeys = hdr[0], nvalues = hdr[1], batch = hdr[2] ? hdr[2] : (1u << 20);
+        if (mcb200_db_part_begin(m.db_, partId, nkeys, nvalues, m.maxLoadFactor_)) throw_last("read_binary");
+        std::vector<Key> keys; std::vector<bucket_size_type> sizes; std::vector<std::uint64_t> vals;
+        for (std::uint64_t done = 0; done < nkeys; ) {
+            const std::uint64_t b = std::min<std::uint64_t>(batch, nkeys - done);
+            keys.resize(b); sizes.resize(b);
+            is.read(reinterpret_cast<char*>(keys.data()), b * sizeof(Key));
+            is.read(reinterpret_cast<char*>(sizes.data()), b);
+            std::uint64_t nv = 0;
+            for (auto s : sizes) nv += s;
+            vals.resize(nv);
+            is.read(reinterpret_cast<char*>(vals.data()), nv * 8);
+            if (!is) throw std::runtime_error("database part is truncated");
+            if (mcb200_db_part_append(m.db_, partId, keys.data(), sizes.data(), vals.data(), b, nv)) throw_last("read_binary");
+            done += b;
+        }
+        if (mcb200_db_part_finish(m.db_, partId)) throw_last("read_binary");
+    }
+
+    /** copy_target_lineages_to_gpus (gpu_hashmap.cuh): kept on the host for `tax` pointers;
+     *  the device gets the per-target key at the rank given to query_async */
+    void copy_target_lineages_to_gpus (const std::vector<ranked_lineage>& lins) { lineages_ = lins; taxRank_ = -1; }
+
+    //--- the query entry point (gpu_hashmap.cu:1299-1313) ---
+    void query_async (query_batch<ValueT>& batch, part_id hostId, const sketching_opt& sk,
+                      taxon_rank lowestRank) const;
+
+    const void* taxon_of (target_id tgt, taxon_rank lowest) const noexcept {
+        if (tgt >= lineages_.size()) return nullptr;
+        for (int r = lowest; r < 21; ++r) if (lineages_[tgt][r]) return lineages_[tgt][r];   // taxonomy.hpp:1260-1267
+        return nullptr;
+    }
+
+    //--- statistics / parameters (gpu_hashmap.cuh:131-311) ---
+    feature_count_type key_count () const noexcept   { return sum(&mcb200_db_key_count); }
+    feature_count_type value_count () const noexcept { return sum(&mcb200_db_value_count); }
+    feature_count_type bucket_count () const noexcept { return sum(&mcb200_db_bucket_count); }
+    feature_count_type dead_feature_count () const noexcept { return 0; }
+    bool empty () const noexcept { return key_count() == 0; }
+    static bucket_size_type max_supported_locations_per_feature () noexcept { return bucket_size_type(mcb200_max_supported_locations_per_feature()); }
+    void max_locations_per_feature (bucket_size_type n) { maxLoc_ = n < 1 ? 1 : (n > 254 ? 254 : n); }
+    bucket_size_type max_locations_per_feature () const noexcept { return maxLoc_; }
+    void max_load_factor (float lf) { maxLoadFactor_ = lf; }
+    float max_load_factor () const noexcept { return maxLoadFactor_ > 0 ? maxLoadFactor_ : 0.5f; }
+    void clear () { if (db_) { const part_id n = table_count(); mcb200_db_close(db_); db_ = mcb200_db_open(device_, n ? n : 1); } }
+    void clear_without_deallocation () { clear(); }
+
+    //--- build side: out of scope ---
+    void initialize_tables (part_id) { out_of_scope(); }
+    template <class Seq> window_id add_target (part_id, const Seq&, target_id, const sketching_opt&) { out_of_scope(); return 0; }
+    void wait_until_add_target_complete (part_id, const sketching_opt&) {}
+    bool add_target_failed (part_id) const noexcept { return false; }
+    bool check_load_factor (part_id) const noexcept { return true; }
+
+    mcb200_db* handle () const noexcept { return db_; }
+    int device () const noexcept { return device_; }
+
+private:
+    template <class F> feature_count_type sum (F f) const noexcept {
+        feature_count_type s = 0;
+        for (part_id p = 0; p < table_count(); ++p) s += f(db_, p);
+        return s;
+    }
+    [[noreturn]] static void out_of_scope () { throw std::logic_error("libmcb200 implements the query path only"); }
+
+    int device_;
+    mcb200_db* db_ = nullptr;
+    float maxLoadFactor_ = 0.f;
+    bucket_size_type maxLoc_ = 254;
+    std::vector<ranked_lineage> lineages_;
+    mutable taxon_rank taxRank_ = 0;     // rank whose keys are on the device (0 = sequence: none needed)
+    friend class query_batch<ValueT>;
+};
+
+//-----------------------------------------------------------------------------
+/** query_batch<Location> (query_batch.cuh:46-449) */
+template <class Location = location>
+class query_batch
+{
+public:
+    using index_type    = std::uint32_t;
+    using size_type     = std::uint32_t;
+    using location_type = Location;
+
+    /** query_batch.cuh:60-259 */
+    class query_host_data {
+    public:
+        index_type num_queries () const noexcept { return mcb200_batch_num_queries(b_, slot_); }
+        index_type num_windows () const noexcept { return numWindows_; }
+        void wait_for_results () {
+            if (mcb200_batch_wait(b_, slot_)) throw_last("wait_for_results");
+            // candidates with the host-only taxon pointer (the reference's kernel writes it on the GPU)
+            const index_type n = num_queries();
+            cands_.resize(std::size_t(n) * maxCand_);
+            for (index_type q = 0; q < n; ++q) {
+                const mcb200_candidate* c = mcb200_batch_top_candidates(b_, slot_, q);
+                for (size_type i = 0; i < maxCand_; ++i) {
+                    match_candidate& m = cands_[std::size_t(q) * maxCand_ + i];
+                    m.tgt = c[i].tgt; m.hits = c[i].hits; m.pos.beg = c[i].beg; m.pos.end = c[i].end;
+                    m.tax = (c[i].hits && store_) ? store_->taxon_of(c[i].tgt, lowest_) : nullptr;
+                }
+            }
+        }
+        span<location_type> allhits (index_type id) const noexcept {
+            std::uint64_t n = 0;
+            const std::uint64_t* p = mcb200_batch_allhits(b_, slot_, id, &n);
+            return span<location_type>{reinterpret_cast<const location_type*>(p), std::size_t(n)};
+        }
+        span<match_candidate> top_candidates (index_type id) const noexcept {
+            if (id >= num_queries() || cands_.empty()) return {};
+            return span<match_candidate>{cands_.data() + std::size_t(id) * maxCand_, maxCand_};
+        }
+        void clear () noexcept { mcb200_batch_clear(b_, slot_); numWindows_ = 0; }
+        void lowest_rank (int r) noexcept { lowest_ = r; }
+    private:
+        friend class query_batch;
+        mcb200_batch* b_ = nullptr; part_id slot_ = 0; size_type maxCand_ = 2;
+        index_type numWindows_ = 0;
+        const gpu_hashmap<feature, Location>* store_ = nullptr; int lowest_ = 0;
+        std::vector<match_candidate> cands_;
+    };
+
+    /** query_batch.cuh:346-354; the last argument is ours: defaults to gpu_hashmap::current() */
+    query_batch (index_type maxQueries, size_type maxEncodeLength, size_type /*maxSketchSize*/,
+                 size_type /*maxResultsPerWindow*/, size_type maxCandidatesPerQuery, bool copyAllHits,
+                 part_id numHostThreads, part_id numGPUs, unsigned /*replica*/,
+                 const gpu_hashmap<feature, Location>* store = nullptr)
+        : numGPUs_(numGPUs)
+    {
+        if (!store) store = gpu_hashmap<feature, Location>::current();
+        if (!store || !store->handle()) throw std::runtime_error("query_batch: no feature store loaded");
+        b_ = mcb200_batch_create(store->handle(), maxQueries, maxEncodeLength, maxCandidatesPerQuery,
+                                 copyAllHits, numHostThreads);
+        if (!b_) throw_last("query_batch");
+        host_.resize(numHostThreads);
+        for (part_id i = 0; i < numHostThreads; ++i) {
+            host_[i].b_ = b_; host_[i].slot_ = i; host_[i].maxCand_ = maxCandidatesPerQuery; host_[i].store_ = store;
+        }
+    }
+    query_batch (const query_batch&) = delete;
+    ~query_batch () { if (b_) mcb200_batch_destroy(b_); }
+
+    part_id gpu_count () const noexcept { return numGPUs_; }
+    query_host_data& host_data (part_id hostId) noexcept { return host_[hostId]; }
+
+    /** query_batch.cuh:383-391 / 85-186: false = batch full, nothing added */
+    template <class Sequence>
+    bool add_paired_read (part_id hostId, const Sequence& seq1, const Sequence& seq2,
+                          const sketching_opt& sk, const candidate_generation_rules& rules)
+    {
+        const int rc = mcb200_batch_add_read(b_, hostId, seq1.data(), seq1.size(), seq2.data(), seq2.size(),
+                                             rules.maxWindowsInRange);
+        if (rc < 0) throw_last("add_paired_read");
+        if (rc == 1) host_[hostId].numWindows_ += windows_of(seq1.size(), sk) + windows_of(seq2.size(), sk);
+        return rc == 1;
+    }
+
+    mcb200_batch* handle () const noexcept { return b_; }
+
+private:
+    static index_type windows_of (std::size_t len, const sketching_opt& sk) noexcept {
+        // windows the reference's batch counts (query_batch.cuh:121-124); at least one per query
+        return len >= sk.kmerlen ? index_type((len - sk.kmerlen + sk.winstride) / sk.winstride) : 0;
+    }
+    mcb200_batch* b_ = nullptr;
+    part_id numGPUs_;
+    std::vector<query_host_data> host_;
+    template <class K, class V> friend class gpu_hashmap;
+};
+
+template <class Key, class ValueT>
+void gpu_hashmap<Key, ValueT>::query_async (query_batch<ValueT>& batch, part_id hostId,
+                                            const sketching_opt& sk, taxon_rank lowestRank) const
+{
+    // `-lowest` above sequence: per-target taxon keys at that rank (candidate_generation.hpp:184-191)
+    if (lowestRank != taxRank_) {
+        if (lowestRank <= 0) { if (mcb200_db_set_target_taxa(db_, nullptr, 0)) throw_last("query_async"); }
+        else {
+            std::vector<std::uint64_t> keys(lineages_.size());
+            for (std::size_t t = 0; t < keys.size(); ++t)
+                keys[t] = reinterpret_cast<std::uintptr_t>(taxon_of(target_id(t), lowestRank));
+            if (mcb200_db_set_target_taxa(db_, keys.data(), std::uint32_t(keys.size()))) throw_last("query_async");
+        }
+        taxRank_ = lowestRank;
+    }
+    batch.host_data(hostId).lowest_rank(lowestRank);
+    const mcb200_sketching s{sk.kmerlen, sk.sketchlen, sk.winlen, sk.winstride};
+    if (mcb200_batch_submit(batch.handle(), hostId, &s)) throw_last("query_async");
+}
+
+} // namespace mcb200
+
+#endif

@@ -22,6 +22,14 @@ SUB_5PCT = 3277
 N_01PCT = 66
 
 
+def _mix_seed(seed: int, stream: int) -> int:
+    """host-side splitmix64 of (seed, stream): well separated key spaces for nearby seeds"""
+    z = (seed * 0x9E3779B97F4A7C15 + stream * 0xD1B54A32D192ED03 + _C0) & _M64
+    z = ((z ^ (z >> 30)) * _C1) & _M64
+    z = ((z ^ (z >> 27)) * _C2) & _M64
+    return z ^ (z >> 31)
+
+
 def _s64(x: int) -> int:
     x &= _M64
     return x - (1 << 64) if x >= (1 << 63) else x
@@ -120,9 +128,9 @@ def target_codes(B, t0: int, t1: int, target_len: int, family: int, seed: int, d
     pos = B.arange(target_len, device)
     tid = B.arange(n, device) + B.u(t0)
     fam = (tid // family) if B is _T else (tid // np.uint64(family))
-    key_root = (fam[:, None] << (32 if B is _T else np.uint64(32))) + pos[None, :] + B.u(seed)
+    key_root = (fam[:, None] << (32 if B is _T else np.uint64(32))) + pos[None, :] + B.u(_mix_seed(seed, 1))
     root = B.sm(key_root) & (3 if B is _T else np.uint64(3))
-    key_mut = (tid[:, None] << (32 if B is _T else np.uint64(32))) + pos[None, :] + B.u(seed * 7919 + 0x5DEECE66D)
+    key_mut = (tid[:, None] << (32 if B is _T else np.uint64(32))) + pos[None, :] + B.u(_mix_seed(seed, 2))
     return _mutate(B, root, B.sm(key_mut), SUB_1PCT)
 
 
@@ -149,11 +157,11 @@ def _reads_chunk(B, lut, comp, targets, n_targets, target_len, i0, i1, read_len,
                  n_thresh, frac_random_65536, device=None):
     n = i1 - i0
     idx = B.arange(n, device) + B.u(i0)
-    h = B.sm(idx + B.u(seed))
+    h = B.sm(idx + B.u(_mix_seed(seed, 3)))
     low16 = h & (0xFFFF if B is _T else np.uint64(0xFFFF))
     is_random = low16 < (frac_random_65536 if B is _T else np.uint64(frac_random_65536))
     strand = B.shr(h, 16) & (1 if B is _T else np.uint64(1))
-    h1 = B.sm(idx + B.u(seed * 31 + 17))
+    h1 = B.sm(idx + B.u(_mix_seed(seed, 4)))
     tgt = B.mod(B.shr(h1, 1), n_targets)
     off = B.mod(B.shr(B.sm(h1), 1), target_len - read_len + 1)
     j = B.arange(read_len, device)
@@ -169,7 +177,7 @@ def _reads_chunk(B, lut, comp, targets, n_targets, target_len, i0, i1, read_len,
         raw = targets[src.astype(np.int64)]
         base = np.where(fwd, raw, comp[raw])
         codes = lut[base].astype(np.uint64)
-    hb = B.sm((idx[:, None] << (12 if B is _T else np.uint64(12))) + j[None, :] + B.u(seed * 131 + 7))
+    hb = B.sm((idx[:, None] << (12 if B is _T else np.uint64(12))) + j[None, :] + B.u(_mix_seed(seed, 5)))
     rnd = B.shr(hb, 48) & (3 if B is _T else np.uint64(3))
     codes = B.where(is_random[:, None], rnd, _mutate(B, codes, hb, sub_thresh))
     isn = (B.shr(hb, 32) & (0xFFFF if B is _T else np.uint64(0xFFFF))) < (n_thresh if B is _T else np.uint64(n_thresh))

@@ -293,3 +293,28 @@ def test_fast_kernel_small_table_overflows_to_cta_kernel(g1):
         tl = [tuple(int(x) for x in row) for row in got[i] if row[1] > 0]
         assert tl == exp.top[i], i
     L.mcb200_workspace_destroy(ws)
+
+
+def test_cpp_shim_runs_the_reference_call_sequence(g1, tmp_path):
+    """metacache_b200/host/shim_query.cpp = database_query.hpp:87-124 written against the C++
+    shims (gpu_hashmap / query_batch mirrors); its output must equal the reference's"""
+    import subprocess
+    from metacache_b200 import dbformat
+    from oracle import refio
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metacache_b200", "host", "shim_query")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    dbp = str(tmp_path / "g1.cache0")
+    dbformat.write_cache(dbp, dbformat.CachePart(g1.keys, g1.sizes, g1.values))
+    rp = str(tmp_path / "reads.txt")
+    norm = lambda x: x if len(x) else b"-"
+    refio.write_reads_txt(rp, [(norm(a), norm(b)) if len(b) else norm(a) for a, b in g1.reads])
+    out = subprocess.run([exe, dbp, rp, "2", "1"], check=True, capture_output=True, text=True).stdout.splitlines()
+    exp = g1.expected("c2_")
+    assert len(out) == len(g1.reads)
+    for i, line in enumerate(out):
+        qid, tops, nall = line.split("\t")
+        assert int(qid) == i
+        got = [tuple(int(x) for x in t.split(":")) for t in tops.split(",")] if tops else []
+        assert got == exp.top[i], i
+        assert int(nall) == len(exp.allhits[i]), i
