@@ -78,7 +78,9 @@ void         mcb200_db_close (mcb200_db* db);
  * (hash_multimap.hpp:1037-1082): begin(nkeys,nvalues) -> append(batch)* ->
  * finish.  `values` are locations as stored on disk ({u32 win,u32 tgt} pairs
  * == u64 (tgt<<32)|win).  Host pointers.  max_load_factor <= 0 selects the
- * default (0.5; gpu_hashmap.cuh max_load_factor()).                          */
+ * default (0.25 while the slots take < 1/6 of the free device memory, else
+ * 0.5; gpu_hashmap.cuh max_load_factor()).  finish() packs the locations to
+ * 32 bits when target and window ids allow and aligns buckets to 64-byte lines. */
 int mcb200_db_part_begin  (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues,
                            float max_load_factor);
 int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,

@@ -74,7 +74,10 @@ template <class T> struct PinBuf {
 struct Part {
     Bucket*   buckets = nullptr;
     uint64_t  nbuckets = 0;
-    uint64_t* values = nullptr;
+    uint64_t* values = nullptr;              // raw u64 locations while loading
+    void*     packed = nullptr;              // final layout (table_finalize)
+    uint64_t  packed_bytes = 0;
+    uint32_t  win_bits = 0;
     uint64_t  nkeys = 0, nvalues = 0;        // declared
     uint64_t  keys_loaded = 0, values_loaded = 0;
     bool      begun = false, finished = false;
@@ -135,6 +138,7 @@ extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
 static void free_part (Part& p) {
     if (p.buckets) cudaFree(p.buckets);
     if (p.values) cudaFree(p.values);
+    if (p.packed) cudaFree(p.packed);
     p = Part{};
 }
 
@@ -161,7 +165,12 @@ extern "C" int mcb200_db_part_begin (mcb200_db* db, uint32_t part, uint64_t nkey
     Part& p = db->parts[part];
     free_part(p);
     float lf = max_load_factor;
-    if (!(lf > 0.f)) lf = 0.5f;
+    if (!(lf > 0.f)) {
+        // 180 GB of HBM: spend it on shorter probe sequences when the table is small enough
+        size_t free_b = 0, total_b = 0;
+        lf = 0.5f;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && double(nkeys) * 16.0 / 0.25 < double(free_b) / 6.0) lf = 0.25f;
+    }
     if (lf > 0.95f) lf = 0.95f;
     const double slots = double(nkeys) / lf;
     p.nbuckets = std::max<uint64_t>(uint64_t(slots / 2.0) + 1, 16);
@@ -235,6 +244,10 @@ extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
         return fail(MCB200_EINVAL, "part %u: loaded %llu/%llu keys, %llu/%llu values", part,
                     (unsigned long long)p.keys_loaded, (unsigned long long)p.nkeys,
                     (unsigned long long)p.values_loaded, (unsigned long long)p.nvalues);
+    if (table_finalize(p.buckets, p.nbuckets, p.values, p.values_loaded, p.packed, p.packed_bytes, p.win_bits,
+                       db->stream) != 0)
+        return fail(MCB200_ECUDA, "part %u: layout finalisation failed: %s", part, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(p.values); p.values = nullptr;
     p.finished = true;
     return 0;
 }
@@ -289,7 +302,7 @@ extern "C" uint64_t mcb200_db_bucket_count (const mcb200_db* db, uint32_t part) 
 extern "C" uint64_t mcb200_db_device_bytes (const mcb200_db* db, uint32_t part) {
     if (!db || part >= db->parts.size()) return 0;
     const Part& p = db->parts[part];
-    return p.nbuckets * sizeof(Bucket) + (p.nvalues + 4) * 8;
+    return p.nbuckets * sizeof(Bucket) + (p.finished ? p.packed_bytes : (p.nvalues + 4) * 8);
 }
 extern "C" int mcb200_db_device (const mcb200_db* db) { return db ? db->device : -1; }
 
@@ -298,7 +311,7 @@ extern "C" int mcb200_db_part_export (const mcb200_db* db, uint32_t part, uint32
     CHECK_DB(db, part);
     const Part& p = db->parts[part];
     if (!p.finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
-    if (table_export(p.buckets, p.nbuckets, p.values, p.keys_loaded, p.values_loaded, keys, sizes,
+    if (table_export(p.buckets, p.nbuckets, p.packed, p.win_bits, p.keys_loaded, p.values_loaded, keys, sizes,
                      values, db->stream) != 0)
         return fail(MCB200_ECUDA, "export failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
@@ -505,7 +518,7 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
     a.feats = ws->feats.p; a.qry_win_off = ws->qry_win_off.p; a.max_win = ws->q.max_win;
     a.tax_of_tgt = ws->db->d_tax; a.n_tax = ws->db->n_tax;
     a.nq = ws->q.n_queries; a.s = ws->sk.s; a.maxc = ws->maxc;
-    a.table = TableView{p.buckets, p.nbuckets, p.values};
+    a.table = TableView{p.buckets, p.nbuckets, p.packed, p.win_bits};
     a.top = d_top;
     a.allhits = nullptr; a.allhits_off = nullptr;
     a.heavy_list = ws->heavy_list.p; a.heavy_count = ws->heavy_count.p;

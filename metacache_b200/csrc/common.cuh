@@ -49,8 +49,10 @@ __host__ __device__ __forceinline__ uint64_t bucket_of (uint32_t key, uint64_t n
 // ---- 16-byte table slot -----------------------------------------------------
 //   key   : feature
 //   meta  : bucket size in bits 0..7 (0 = empty slot, 1..254 = locations)
-//   data  : size == 1 -> the location itself (inline);  else index of the first
-//           location in the part's `values` array
+//   data  : 64-bit locations: size == 1 -> the location itself (inline)
+//           32-bit packed locations: size <= 2 -> the locations themselves
+//           else index (in elements) of the bucket's first location in `values`,
+//           which starts on a 64-byte boundary (one memory request per line)
 // Two slots share one 32-byte DRAM sector ("bucket"); a lookup reads whole
 // sectors with one 256-bit load.
 struct __align__(16) Slot {
@@ -63,8 +65,25 @@ struct __align__(32) Bucket { Slot s[2]; };
 struct TableView {
     const Bucket*   buckets;
     uint64_t        nbuckets;
-    const uint64_t* values;
+    const void*     values;     // u32 (win_bits != 0) or u64 locations, buckets 64-byte aligned
+    uint32_t        win_bits;   // packed location = (tgt << win_bits) | win;  0 = 64-bit locations
 };
+
+__host__ __device__ __forceinline__ uint64_t unpack_loc (uint32_t l, uint32_t win_bits) {
+    return (uint64_t(l >> win_bits) << 32) | (l & ((1u << win_bits) - 1u));
+}
+// number of locations stored inside the slot itself
+__host__ __device__ __forceinline__ uint32_t inline_capacity (uint32_t win_bits) { return win_bits ? 2u : 1u; }
+
+// i-th location of a bucket as u64 (tgt << 32 | win)
+__device__ __forceinline__ uint64_t bucket_loc (const TableView& t, uint64_t data, uint32_t size, uint32_t i) {
+    if (t.win_bits) {
+        const uint32_t l = (size <= 2) ? uint32_t(data >> (32 * i))
+                                       : __ldg(static_cast<const uint32_t*>(t.values) + data + i);
+        return unpack_loc(l, t.win_bits);
+    }
+    return (size == 1) ? data : __ldg(static_cast<const uint64_t*>(t.values) + data + i);
+}
 
 __device__ __forceinline__ void load_bucket (const Bucket* p, Slot& a, Slot& b) {
     // one 32-byte sector, read-only path, 256-bit vector load (sm_100+)

@@ -42,9 +42,12 @@ void device_scan_u32 (const uint32_t* in, uint32_t* out, uint64_t n, void*& tmp,
 void device_scan_u64 (const uint64_t* in, uint64_t* out, uint64_t n, void*& tmp, size_t& tmp_bytes,
                       cudaStream_t st);
 // export: occupied slots in table order -> keys/sizes/value runs
-int  table_export (const Bucket* buckets, uint64_t nbuckets, const uint64_t* values,
+int  table_export (const Bucket* buckets, uint64_t nbuckets, const void* values, uint32_t win_bits,
                    uint64_t nkeys, uint64_t nvalues, uint32_t* h_keys, uint8_t* h_sizes,
                    uint64_t* h_values, cudaStream_t st);
+// after all batches are inserted: pack + align the locations, rewrite the slots' data words
+int  table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_values, uint64_t nvalues,
+                     void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st);
 // build from (feature, location) pairs produced by sketching targets
 struct BuiltPart { uint32_t* keys; uint8_t* sizes; uint64_t* values; uint64_t nkeys, nvalues; };
 int  build_from_sketches (const uint32_t* feats, const uint32_t* win_seq, const uint32_t* seq_win_off,

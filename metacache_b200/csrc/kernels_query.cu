@@ -284,8 +284,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
                     for (uint32_t step = 16; step > 0; step >>= 1)
                         if (sbase[b + step] <= p) b += step;
                     const uint32_t sb = sbase[b];
-                    const uint64_t d = sdata[b];
-                    v[u] = (sbase[b + 1] - sb == 1) ? d : __ldg(a.table.values + d + (p - sb));
+                    v[u] = bucket_loc(a.table, sdata[b], sbase[b + 1] - sb, p - sb);
                 }
             }
             #pragma unroll
@@ -409,7 +408,7 @@ query_warp_kernel (QueryArgs a, uint32_t T)
             for (uint32_t r = 0; r < rounds; ++r) {
                 if (*reinterpret_cast<volatile uint32_t*>(misc) > dmax) { overflow = true; break; }
                 if (r < own) {
-                    const uint64_t v = (size == 1) ? data : a.table.values[data + r];
+                    const uint64_t v = bucket_loc(a.table, data, size, r);
                     agg_insert(hkeys, hcnt, mask, v, misc);
                 }
                 __syncwarp();
@@ -423,7 +422,7 @@ query_warp_kernel (QueryArgs a, uint32_t T)
                 const uint64_t bof = __shfl_sync(kFull, data, src);
                 for (uint32_t i = 0; i < bsz; i += 32) {
                     if (*reinterpret_cast<volatile uint32_t*>(misc) > dmax) { overflow = true; break; }
-                    if (i + lane < bsz) agg_insert(hkeys, hcnt, mask, __ldg(a.table.values + bof + i + lane), misc);
+                    if (i + lane < bsz) agg_insert(hkeys, hcnt, mask, bucket_loc(a.table, bof, bsz, i + lane), misc);
                     __syncwarp();
                 }
             }
@@ -711,9 +710,7 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
                 for (uint32_t step = kHeavyThreads / 2; step > 0; step >>= 1)
                     if (s_base[b + step] <= p) b += step;
                 const uint32_t sb = s_base[b];
-                const uint32_t sz = s_base[b + 1] - sb;
-                const uint64_t d = s_data[b];
-                keys[p] = (sz == 1) ? d : a.table.values[d + (p - sb)];
+                keys[p] = bucket_loc(a.table, s_data[b], s_base[b + 1] - sb, p - sb);
             }
             __syncthreads();
             filled += total;

@@ -9,6 +9,7 @@
 //   serialize               hash_multimap.hpp:1037-1082
 #include "internal.h"
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <vector>
 
 namespace mcb {
@@ -125,7 +126,7 @@ __global__ void slot_sizes_kernel (const Bucket* __restrict__ buckets, uint64_t 
 }
 
 __global__ void slot_export_kernel (const Bucket* __restrict__ buckets, uint64_t nslots,
-                                    const uint64_t* __restrict__ values,
+                                    TableView view,
                                     const uint32_t* __restrict__ key_pos,
                                     const uint64_t* __restrict__ val_pos,
                                     uint32_t* __restrict__ out_keys, uint8_t* __restrict__ out_sizes,
@@ -140,8 +141,7 @@ __global__ void slot_export_kernel (const Bucket* __restrict__ buckets, uint64_t
     out_keys[kp] = s.key;
     out_sizes[kp] = uint8_t(size);
     uint64_t* dst = out_values + val_pos[i];
-    if (size == 1) dst[0] = s.data;
-    else for (uint32_t j = 0; j < size; ++j) dst[j] = values[s.data + j];
+    for (uint32_t j = 0; j < size; ++j) dst[j] = bucket_loc(view, s.data, size, j);
 }
 
 __global__ void widen_kernel (const uint32_t* in, uint64_t* out, uint64_t n) {
@@ -149,10 +149,11 @@ __global__ void widen_kernel (const uint32_t* in, uint64_t* out, uint64_t n) {
     if (i < n) out[i] = in[i];
 }
 
-int table_export (const Bucket* buckets, uint64_t nbuckets, const uint64_t* values,
+int table_export (const Bucket* buckets, uint64_t nbuckets, const void* values, uint32_t win_bits,
                   uint64_t nkeys, uint64_t nvalues, uint32_t* h_keys, uint8_t* h_sizes,
                   uint64_t* h_values, cudaStream_t st)
 {
+    const TableView view{buckets, nbuckets, values, win_bits};
     const uint64_t nslots = nbuckets * 2;
     if (!nslots || !nkeys) return 0;
     uint32_t *occ = nullptr, *sz = nullptr, *kpos = nullptr, *okeys = nullptr;
@@ -169,7 +170,7 @@ int table_export (const Bucket* buckets, uint64_t nbuckets, const uint64_t* valu
     count_launch(2);
     device_scan_u32(occ, kpos, nslots, tmp, tmpb, st);
     device_scan_u64(sz64, vpos, nslots, tmp, tmpb, st);
-    slot_export_kernel<<<grid, 256, 0, st>>>(buckets, nslots, values, kpos, vpos, okeys, osizes, ovals);
+    slot_export_kernel<<<grid, 256, 0, st>>>(buckets, nslots, view, kpos, vpos, okeys, osizes, ovals);
     count_launch();
     cudaMemcpyAsync(h_keys, okeys, nkeys * 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(h_sizes, osizes, nkeys, cudaMemcpyDeviceToHost, st);
@@ -178,6 +179,113 @@ int table_export (const Bucket* buckets, uint64_t nbuckets, const uint64_t* valu
     cudaFree(occ); cudaFree(sz); cudaFree(kpos); cudaFree(sz64); cudaFree(vpos);
     cudaFree(okeys); cudaFree(osizes); cudaFree(ovals); if (tmp) cudaFree(tmp);
     return e == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------
+// final layout of a loaded part: locations packed to 32 bits when target and
+// window ids fit, every non-inline bucket starting on a 64-byte line (one memory
+// request fetches a bucket of up to 16 packed / 8 wide locations)
+// ---------------------------------------------------------------------------
+__global__ void loc_max_kernel (const uint64_t* __restrict__ values, uint64_t n,
+                                uint32_t* __restrict__ max_tgt_win)
+{
+    uint32_t mt = 0, mw = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t v = values[i];
+        mt = max(mt, uint32_t(v >> 32)); mw = max(mw, uint32_t(v));
+    }
+    mt = __reduce_max_sync(kFull, mt); mw = __reduce_max_sync(kFull, mw);
+    if ((threadIdx.x & 31) == 0) { atomicMax(max_tgt_win, mt); atomicMax(max_tgt_win + 1, mw); }
+}
+
+__global__ void slot_caps_kernel (const Bucket* __restrict__ buckets, uint64_t nslots,
+                                  uint32_t inline_cap, uint32_t line_elems, uint64_t* __restrict__ caps)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i > nslots) return;
+    uint64_t c = 0;
+    if (i < nslots) {
+        const uint32_t size = reinterpret_cast<const Slot*>(buckets)[i].meta & 0xFFu;
+        if (size > inline_cap) c = (uint64_t(size) + line_elems - 1) / line_elems * line_elems;
+    }
+    caps[i] = c;                                  // caps[nslots] = 0: the scan leaves the total there
+}
+
+__global__ void slot_relayout_kernel (Bucket* __restrict__ buckets, uint64_t nslots,
+                                      const uint64_t* __restrict__ raw, void* __restrict__ packed,
+                                      const uint64_t* __restrict__ new_off, uint32_t win_bits)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    Slot* sl = reinterpret_cast<Slot*>(buckets) + i;
+    const uint32_t size = sl->meta & 0xFFu;
+    if (size == 0) return;
+    const uint64_t data = sl->data;
+    auto pack = [win_bits] (uint64_t v) { return (uint32_t(v >> 32) << win_bits) | uint32_t(v); };
+    if (win_bits) {
+        if (size == 1) sl->data = pack(data);
+        else if (size == 2) sl->data = uint64_t(pack(raw[data])) | (uint64_t(pack(raw[data + 1])) << 32);
+        else {
+            uint32_t* dst = static_cast<uint32_t*>(packed) + new_off[i];
+            for (uint32_t j = 0; j < size; ++j) dst[j] = pack(raw[data + j]);
+            sl->data = new_off[i];
+        }
+    } else if (size > 1) {
+        uint64_t* dst = static_cast<uint64_t*>(packed) + new_off[i];
+        for (uint32_t j = 0; j < size; ++j) dst[j] = raw[data + j];
+        sl->data = new_off[i];
+    }
+}
+
+static uint32_t bits_for (uint32_t maxval) { uint32_t b = 1; while (b < 32 && (maxval >> b)) ++b; return b; }
+
+int table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_values, uint64_t nvalues,
+                    void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st)
+{
+    packed = nullptr; packed_bytes = 0; win_bits = 0;
+    const uint64_t nslots = nbuckets * 2;
+    uint32_t* d_max = nullptr; uint64_t* caps = nullptr;
+    void* tmp = nullptr; size_t tmpb = 0;
+    int rc = -1;
+    uint32_t h_max[2] = {0, 0};
+    uint64_t total = 0;
+    if (cudaMalloc(&d_max, 8) != cudaSuccess) goto done;
+    if (cudaMemsetAsync(d_max, 0, 8, st) != cudaSuccess) goto done;
+    if (nvalues) {
+        loc_max_kernel<<<148 * 8, 256, 0, st>>>(raw_values, nvalues, d_max);
+        count_launch();
+    }
+    if (cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) goto done;
+    if (cudaStreamSynchronize(st) != cudaSuccess) goto done;
+    {
+        const uint32_t tb = bits_for(h_max[0]), wb = bits_for(h_max[1]);
+        win_bits = (tb + wb <= 32) ? wb : 0u;
+        if (getenv("MCB200_WIDE_LOCATIONS")) win_bits = 0;        // testing aid: force 64-bit locations
+    }
+    {
+        const uint32_t line_elems = win_bits ? 16u : 8u;
+        if (cudaMalloc(&caps, (nslots + 1) * 8) != cudaSuccess) goto done;
+        slot_caps_kernel<<<unsigned((nslots + 1 + 255) / 256), 256, 0, st>>>(buckets, nslots, inline_capacity(win_bits),
+                                                                            line_elems, caps);
+        count_launch();
+        device_scan_u64(caps, caps, nslots + 1, tmp, tmpb, st);
+        if (cudaMemcpyAsync(&total, caps + nslots, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) goto done;
+        if (cudaStreamSynchronize(st) != cudaSuccess) goto done;
+        packed_bytes = (total + line_elems) * (win_bits ? 4 : 8);
+        if (cudaMalloc(&packed, packed_bytes) != cudaSuccess) { packed = nullptr; goto done; }
+        if (cudaMemsetAsync(packed, 0xFF, packed_bytes, st) != cudaSuccess) goto done;
+        slot_relayout_kernel<<<unsigned((nslots + 255) / 256), 256, 0, st>>>(buckets, nslots, raw_values, packed,
+                                                                            caps, win_bits);
+        count_launch();
+        if (cudaStreamSynchronize(st) != cudaSuccess) goto done;
+    }
+    rc = 0;
+done:
+    if (d_max) cudaFree(d_max);
+    if (caps) cudaFree(caps);
+    if (tmp) cudaFree(tmp);
+    if (rc && packed) { cudaFree(packed); packed = nullptr; }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

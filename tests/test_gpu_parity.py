@@ -318,3 +318,34 @@ def test_cpp_shim_runs_the_reference_call_sequence(g1, tmp_path):
         got = [tuple(int(x) for x in t.split(":")) for t in tops.split(",")] if tops else []
         assert got == exp.top[i], i
         assert int(nall) == len(exp.allhits[i]), i
+
+
+def test_wide_location_layout_gives_identical_results(g1, monkeypatch):
+    """tables are stored with 32-bit packed locations when ids fit; the 64-bit layout (forced
+    here) must behave identically"""
+    from metacache_b200.database import Database, query_reads
+    monkeypatch.setenv("MCB200_WIDE_LOCATIONS", "1")
+    db = Database(0, 1)
+    db.load_part_arrays(0, g1.keys, g1.sizes, g1.values)
+    monkeypatch.delenv("MCB200_WIDE_LOCATIONS")
+    exp = g1.expected("c2_")
+    res = query_reads(db, g1.reads, _sk(g1), copy_all_hits=True)
+    for i, (allh, top) in enumerate(res):
+        assert np.array_equal(allh, exp.allhits[i]), i
+        assert top == exp.top[i], i
+    res = query_reads(db, g1.reads, _sk(g1), copy_all_hits=False)
+    assert [r[1] for r in res] == exp.top
+    k, s, v = db.export_part(0)
+    o, ro = np.argsort(k), np.argsort(g1.keys)
+    assert np.array_equal(k[o], g1.keys[ro]) and np.array_equal(s[o], g1.sizes[ro])
+    db.close()
+
+
+def test_export_round_trip_packed_layout(g1):
+    k, s, v = g1.db.export_part(0)
+    o, ro = np.argsort(k), np.argsort(g1.keys)
+    assert np.array_equal(k[o], g1.keys[ro]) and np.array_equal(s[o], g1.sizes[ro])
+    offs = np.zeros(len(s) + 1, np.int64); np.cumsum(s, out=offs[1:])
+    roffs = np.zeros(len(g1.sizes) + 1, np.int64); np.cumsum(g1.sizes, out=roffs[1:])
+    for a, b in zip(o, ro):
+        assert np.array_equal(v[offs[a]:offs[a + 1]], g1.values[roffs[b]:roffs[b + 1]])
