@@ -194,49 +194,81 @@ __device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint
 constexpr uint32_t kMaxLookupW = 8;
 constexpr uint32_t kMaxProbe   = 48;
 
+// Key type of the aggregation table: the table's own 32-bit packed location when the part is
+// stored packed (order preserving: (tgt << win_bits) | win), else the u64 location.
+template <class K> struct AggKey;
+template <> struct AggKey<uint32_t> {
+    static constexpr uint32_t kEmpty = 0xFFFFFFFFu;          // packed locations keep the top bit clear
+    __device__ static __forceinline__ uint32_t hash (uint32_t k) { const uint32_t h = k * 0x9E3779B1u; return h ^ (h >> 15); }
+    __device__ static __forceinline__ uint32_t load (const TableView& t, uint64_t data, uint32_t size, uint32_t i) {
+        return (size <= 2) ? uint32_t(data >> (32 * i)) : __ldg(static_cast<const uint32_t*>(t.values) + data + i);
+    }
+    __device__ static __forceinline__ uint32_t win (uint32_t k, uint32_t wb) { return k & ((1u << wb) - 1u); }
+    __device__ static __forceinline__ uint32_t tgt (uint32_t k, uint32_t wb) { return k >> wb; }
+    __device__ static __forceinline__ uint32_t cas (uint32_t* p, uint32_t v) { return atomicCAS(p, kEmpty, v); }
+};
+template <> struct AggKey<uint64_t> {
+    static constexpr uint64_t kEmpty = ~0ull;
+    __device__ static __forceinline__ uint32_t hash (uint64_t k) { return loc_hash(k); }
+    __device__ static __forceinline__ uint64_t load (const TableView& t, uint64_t data, uint32_t size, uint32_t i) {
+        return (size == 1) ? data : __ldg(static_cast<const uint64_t*>(t.values) + data + i);
+    }
+    __device__ static __forceinline__ uint32_t win (uint64_t k, uint32_t) { return uint32_t(k); }
+    __device__ static __forceinline__ uint32_t tgt (uint64_t k, uint32_t) { return uint32_t(k >> 32); }
+    __device__ static __forceinline__ uint64_t cas (uint64_t* p, uint64_t v) {
+        return atomicCAS(reinterpret_cast<unsigned long long*>(p), kEmpty, v);
+    }
+};
+
+template <class K>
 __host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
-    // hkeys[T] u64 | hcnt[T] u32 | list[T/2+32] u16 -> hits[T/2+32] u32 | sdata[32] u64 | sbase[34] u32 | misc[34]
-    return size_t(T) * 12 + (size_t(T) / 2 + 32) * 6 + 32 * 8 + 34 * 4 + 34 * 4;
+    // hkeys[T] K | sdata[32] u64 | hcnt[T] u32 | hits[T/2+32] u32 | sbase[34] u32 | misc[34] u32 | list[T/2+32] u16
+    const size_t b = size_t(T) * sizeof(K) + 32 * 8 + size_t(T) * 4 + (size_t(T) / 2 + 32) * 6 + 34 * 4 + 34 * 4;
+    return (b + 15) & ~size_t(15);
 }
 
-__device__ __forceinline__ bool agg_insert_bounded (uint64_t* hkeys, uint32_t* hcnt, uint32_t mask, uint64_t v)
+template <class K>
+__device__ __forceinline__ bool agg_insert_bounded (K* hkeys, uint32_t* hcnt, uint32_t mask, K v)
 {
-    uint32_t h = loc_hash(v) & mask;
+    uint32_t h = AggKey<K>::hash(v) & mask;
     #pragma unroll 1
     for (uint32_t probes = 0; probes < kMaxProbe; ++probes) {
-        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(hkeys + h),
-                                                 kEmptyKey, v);
-        if (old == kEmptyKey || old == v) { atomicAdd(hcnt + h, 1u); return true; }
+        const K old = AggKey<K>::cas(hkeys + h, v);
+        if (old == AggKey<K>::kEmpty || old == v) { atomicAdd(hcnt + h, 1u); return true; }
         h = (h + 1) & mask;
     }
     return false;
 }
 
-__device__ __forceinline__ uint32_t agg_lookup (const uint64_t* hkeys, const uint32_t* hcnt, uint32_t mask, uint64_t k)
+template <class K>
+__device__ __forceinline__ uint32_t agg_lookup (const K* hkeys, const uint32_t* hcnt, uint32_t mask, K k)
 {
-    uint32_t h = loc_hash(k) & mask;
+    uint32_t h = AggKey<K>::hash(k) & mask;
     for (;;) {
-        const uint64_t x = hkeys[h];
+        const K x = hkeys[h];
         if (x == k) return hcnt[h];
-        if (x == kEmptyKey) return 0;
+        if (x == AggKey<K>::kEmpty) return 0;
         h = (h + 1) & mask;
     }
 }
 
+template <class K>
 __global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T)
 {
+    using AK = AggKey<K>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* mine = smem_raw + warp * fast_smem_bytes(T);
-    uint64_t* hkeys = reinterpret_cast<uint64_t*>(mine);
-    uint64_t* sdata = hkeys + T;
-    uint32_t* hcnt  = reinterpret_cast<uint32_t*>(sdata + 32);
-    uint32_t* hits  = hcnt + T;                                   // [T/2+32]
-    uint32_t* sbase = hits + (T / 2 + 32);                        // [34]
-    uint32_t* misc  = sbase + 34;                                 // [0] overflow flag, [1..] chosen
-    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 34);     // [T/2+32]
+    uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T);
+    uint64_t* sdata = reinterpret_cast<uint64_t*>(mine);                       // [32]
+    K*        hkeys = reinterpret_cast<K*>(sdata + 32);                        // [T]
+    uint32_t* hcnt  = reinterpret_cast<uint32_t*>(hkeys + T);                  // [T]
+    uint32_t* hits  = hcnt + T;                                                // [T/2+32]
+    uint32_t* sbase = hits + (T / 2 + 32);                                     // [34]
+    uint32_t* misc  = sbase + 34;                                              // [0] overflow flag, [1..] chosen
+    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 34);                  // [T/2+32]
     const uint32_t mask = T - 1, dmax = T / 2;
+    const uint32_t wb = a.table.win_bits;
 
     const uint32_t q = blockIdx.x * kQWarps + warp;
     if (q >= a.nq) return;
@@ -252,7 +284,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         warp_stats(a, false, 0, 0, 0);
         return;
     }
-    for (uint32_t i = lane; i < T; i += 32) { hkeys[i] = kEmptyKey; hcnt[i] = 0; }
+    for (uint32_t i = lane; i < T; i += 32) { hkeys[i] = AK::kEmpty; hcnt[i] = 0; }
     if (lane == 0) misc[0] = 0;
     __syncwarp();
 
@@ -273,23 +305,23 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         __syncwarp();
         // waves of 4 x 32 locations: issue all loads of a wave, then insert
         for (uint32_t p0 = 0; p0 < total; p0 += 128) {
-            uint64_t v[4];
+            K v[4];
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t p = p0 + u * 32 + lane;
-                v[u] = kEmptyKey;
+                v[u] = AK::kEmpty;
                 if (p < total) {
                     uint32_t b = 0;
                     #pragma unroll
                     for (uint32_t step = 16; step > 0; step >>= 1)
                         if (sbase[b + step] <= p) b += step;
                     const uint32_t sb = sbase[b];
-                    v[u] = bucket_loc(a.table, sdata[b], sbase[b + 1] - sb, p - sb);
+                    v[u] = AK::load(a.table, sdata[b], sbase[b + 1] - sb, p - sb);
                 }
             }
             #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (v[u] != kEmptyKey && !agg_insert_bounded(hkeys, hcnt, mask, v[u])) misc[0] = 1;
+                if (v[u] != AK::kEmpty && !agg_insert_bounded<K>(hkeys, hcnt, mask, v[u])) misc[0] = 1;
         }
         __syncwarp();
         if (*reinterpret_cast<volatile uint32_t*>(misc) != 0) { ok = false; break; }
@@ -304,7 +336,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     uint32_t D = 0;
     if (ok) {
         for (uint32_t base = 0; base < T && D <= dmax; base += 32) {
-            const bool o = hkeys[base + lane] != kEmptyKey;
+            const bool o = hkeys[base + lane] != AK::kEmpty;
             const uint32_t occ = __ballot_sync(kFull, o);
             if (o) list[D + __popc(occ & ((1u << lane) - 1u))] = uint16_t(base + lane);
             D += __popc(occ);
@@ -317,15 +349,14 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         return;
     }
     __syncwarp();
-    // ---- hits(j) and first window of the range, per distinct location ---------
-    // lane-local best over its entries: (hits desc, key asc)
-    uint32_t best_c = 0; uint64_t best_k = kPadKey;
+    // ---- hits(j) per distinct location; lane-local best (hits desc, key asc) ----
+    uint32_t best_c = 0; K best_k = AK::kEmpty;
     for (uint32_t j = lane; j < D; j += 32) {
         const uint32_t slot = list[j];
-        const uint64_t k = hkeys[slot];
+        const K k = hkeys[slot];
         uint32_t c = hcnt[slot];
-        const uint32_t win = uint32_t(k);
-        for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup(hkeys, hcnt, mask, k - d);
+        const uint32_t win = AK::win(k, wb);
+        for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup<K>(hkeys, hcnt, mask, k - d);
         hits[j] = c;
         if (c > best_c || (c == best_c && k < best_k)) { best_c = c; best_k = k; }
     }
@@ -335,10 +366,10 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     uint32_t c = 0;
     for (; c < a.maxc; ++c) {
         if (c > 0) {
-            best_c = 0; best_k = kPadKey;
+            best_c = 0; best_k = AK::kEmpty;
             for (uint32_t j = lane; j < D; j += 32) {
-                const uint64_t k = hkeys[list[j]];
-                const uint32_t tgt = uint32_t(k >> 32);
+                const K k = hkeys[list[j]];
+                const uint32_t tgt = AK::tgt(k, wb);
                 bool taken = false;
                 for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
                 const uint32_t cj = hits[j];
@@ -348,14 +379,17 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         const uint32_t wmax = __reduce_max_sync(kFull, best_c);
         if (wmax == 0) break;
         const bool cand = (best_c == wmax);
-        const uint32_t wt = __reduce_min_sync(kFull, cand ? uint32_t(best_k >> 32) : 0xFFFFFFFFu);
-        const uint32_t ww = __reduce_min_sync(kFull, (cand && uint32_t(best_k >> 32) == wt) ? uint32_t(best_k) : 0xFFFFFFFFu);
+        // smallest key among the lanes holding the maximum: (tgt, win) lexicographic
+        const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
+        const uint32_t wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
+        const uint32_t ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
         if (lane == 0) {
             // first window of the winning range: smallest present window in (ww-W, ww]
-            const uint64_t ke = (uint64_t(wt) << 32) | ww;
+            K ke;
+            if (sizeof(K) == 4) ke = K((wt << wb) | ww); else ke = K((uint64_t(wt) << 32) | ww);
             uint32_t beg = ww;
             for (uint32_t d = 1; d < W && d <= ww; ++d)
-                if (agg_lookup(hkeys, hcnt, mask, ke - d)) beg = ww - d;
+                if (agg_lookup<K>(hkeys, hcnt, mask, ke - d)) beg = ww - d;
             top[c] = mcb200_candidate{wt, wmax, beg, ww};
             chosen[c] = wt;
         }
@@ -581,13 +615,17 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int, cudaStream_t st)
     if (!attr_set) {
         cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(query_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
     if (!a.tax_of_tgt && !a.allhits) {
         // top hits only at rank "sequence": the sort-free kernel
-        query_fast_kernel<<<grid, kQWarps * 32, fast_smem_bytes(T) * kQWarps, st>>>(a, T);
+        if (a.table.win_bits)
+            query_fast_kernel<uint32_t><<<grid, kQWarps * 32, fast_smem_bytes<uint32_t>(T) * kQWarps, st>>>(a, T);
+        else
+            query_fast_kernel<uint64_t><<<grid, kQWarps * 32, fast_smem_bytes<uint64_t>(T) * kQWarps, st>>>(a, T);
     } else {
         const size_t smem = warp_smem_bytes(T) * kQWarps;
         if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T);

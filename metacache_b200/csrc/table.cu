@@ -259,7 +259,7 @@ int table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_valu
     if (cudaStreamSynchronize(st) != cudaSuccess) goto done;
     {
         const uint32_t tb = bits_for(h_max[0]), wb = bits_for(h_max[1]);
-        win_bits = (tb + wb <= 32) ? wb : 0u;
+        win_bits = (tb + wb <= 31) ? wb : 0u;     // top bit stays clear: ~0 is never a packed location
         if (getenv("MCB200_WIDE_LOCATIONS")) win_bits = 0;        // testing aid: force 64-bit locations
     }
     {
