@@ -24,6 +24,7 @@
 // with tgt, "largest hits, smallest j" also realises the stable top-k order
 // (hits desc, arrival = target asc) of insert().
 #include "internal.h"
+#include <algorithm>
 
 namespace mcb {
 
@@ -220,10 +221,14 @@ template <> struct AggKey<uint64_t> {
     }
 };
 
+constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk staged in shared memory
+
 template <class K>
 __host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
-    // hkeys[T] K | sdata[32] u64 | hcnt[T] u32 | hits[T/2+32] u32 | sbase[34] u32 | misc[34] u32 | list[T/2+32] u16
-    const size_t b = size_t(T) * sizeof(K) + 32 * 8 + size_t(T) * 4 + (size_t(T) / 2 + 32) * 6 + 34 * 4 + 34 * 4;
+    // sdata[32] u64 | stage[kStage] K | hkeys[T] K | hcnt[T] u32 | hits[T/2+32] u32 | sbase[36] u32 |
+    // misc[36] u32 | list[T/2+32] u16
+    const size_t b = 32 * 8 + size_t(kStage) * sizeof(K) + size_t(T) * sizeof(K) + size_t(T) * 4
+                   + (size_t(T) / 2 + 32) * 6 + 36 * 4 + 36 * 4;
     return (b + 15) & ~size_t(15);
 }
 
@@ -261,17 +266,20 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T);
     uint64_t* sdata = reinterpret_cast<uint64_t*>(mine);                       // [32]
-    K*        hkeys = reinterpret_cast<K*>(sdata + 32);                        // [T]
+    K*        stage = reinterpret_cast<K*>(sdata + 32);                        // [kStage]
+    K*        hkeys = stage + kStage;                                          // [T]   (16-byte aligned)
     uint32_t* hcnt  = reinterpret_cast<uint32_t*>(hkeys + T);                  // [T]
     uint32_t* hits  = hcnt + T;                                                // [T/2+32]
-    uint32_t* sbase = hits + (T / 2 + 32);                                     // [34]
-    uint32_t* misc  = sbase + 34;                                              // [0] overflow flag, [1..] chosen
-    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 34);                  // [T/2+32]
+    uint32_t* sbase = hits + (T / 2 + 32);                                     // [36]
+    uint32_t* misc  = sbase + 36;                                              // [0] overflow flag, [1..] chosen
+    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 36);                  // [T/2+32]
     const uint32_t mask = T - 1, dmax = T / 2;
     const uint32_t wb = a.table.win_bits;
 
-    const uint32_t q = blockIdx.x * kQWarps + warp;
-    if (q >= a.nq) return;
+    // persistent warps: a warp keeps its shared-memory table and walks the reads with a grid
+    // stride, so warp slots never idle behind the slowest read of a CTA
+    const uint32_t nwarps = gridDim.x * kQWarps;
+    for (uint32_t q = blockIdx.x * kQWarps + warp; q < a.nq; q += nwarps) {
     const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
     const uint32_t nslots = (w1 - w0) * a.s;
     const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
@@ -282,9 +290,15 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
         warp_stats(a, false, 0, 0, 0);
-        return;
+        continue;
     }
-    for (uint32_t i = lane; i < T; i += 32) { hkeys[i] = AK::kEmpty; hcnt[i] = 0; }
+    {   // clear the table with 128-bit stores (hkeys and hcnt are contiguous and 16-byte aligned)
+        const uint4 e4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z4 = make_uint4(0, 0, 0, 0);
+        uint4* k4 = reinterpret_cast<uint4*>(hkeys);
+        uint4* c4 = reinterpret_cast<uint4*>(hcnt);
+        for (uint32_t i = lane; i < T * sizeof(K) / 16; i += 32) k4[i] = e4;
+        for (uint32_t i = lane; i < T / 4; i += 32) c4[i] = z4;
+    }
     if (lane == 0) misc[0] = 0;
     __syncwarp();
 
@@ -299,6 +313,39 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         if (total == 0) continue;
         H += total;
+        if (total <= kStage) {
+            // every lane copies ITS bucket (one 64-byte line per 16 packed / 8 wide locations, 128-bit
+            // loads) to its place in the staging buffer; then the warp inserts the dense list
+            const uint32_t sb = incl - size;
+            if (size) {
+                if (sizeof(K) == 4) {
+                    if (size <= 2) { stage[sb] = K(uint32_t(data)); if (size == 2) stage[sb + 1] = K(uint32_t(data >> 32)); }
+                    else {
+                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(a.table.values) + data);
+                        for (uint32_t i = 0; i < size; i += 4) {
+                            const uint4 x = __ldg(src + (i >> 2));
+                            stage[sb + i] = K(x.x);
+                            if (i + 1 < size) stage[sb + i + 1] = K(x.y);
+                            if (i + 2 < size) stage[sb + i + 2] = K(x.z);
+                            if (i + 3 < size) stage[sb + i + 3] = K(x.w);
+                        }
+                    }
+                } else {
+                    if (size == 1) stage[sb] = K(data);
+                    else {
+                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint64_t*>(a.table.values) + data);
+                        for (uint32_t i = 0; i < size; i += 2) {
+                            const uint4 x = __ldg(src + (i >> 1));
+                            stage[sb + i] = K((uint64_t(x.y) << 32) | x.x);
+                            if (i + 1 < size) stage[sb + i + 1] = K((uint64_t(x.w) << 32) | x.z);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            for (uint32_t p = lane; p < total; p += 32)
+                if (!agg_insert_bounded<K>(hkeys, hcnt, mask, stage[p])) misc[0] = 1;
+        } else {
         sbase[lane] = incl - size;
         sdata[lane] = data;
         if (lane == 31) sbase[32] = total;
@@ -323,6 +370,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
             for (int u = 0; u < 4; ++u)
                 if (v[u] != AK::kEmpty && !agg_insert_bounded<K>(hkeys, hcnt, mask, v[u])) misc[0] = 1;
         }
+        }
         __syncwarp();
         if (*reinterpret_cast<volatile uint32_t*>(misc) != 0) { ok = false; break; }
     }
@@ -330,7 +378,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     if (ok && H == 0) {
         if (lane == 0) write_empty(top, 0, a.maxc);
         warp_stats(a, true, 0, nfeat, sectors);
-        return;
+        continue;
     }
     // ---- distinct locations: compact the occupied slots ----------------------
     uint32_t D = 0;
@@ -346,7 +394,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     if (!ok) {
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
         warp_stats(a, false, 0, nfeat, sectors);
-        return;
+        continue;
     }
     __syncwarp();
     // ---- hits(j) per distinct location; lane-local best (hits desc, key asc) ----
@@ -363,15 +411,15 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     __syncwarp();
     // ---- top-k distinct targets ----------------------------------------------
     uint32_t* chosen = misc + 1;
-    uint32_t c = 0;
+    uint32_t c = 0, last = 0xFFFFFFFFu;
     for (; c < a.maxc; ++c) {
         if (c > 0) {
             best_c = 0; best_k = AK::kEmpty;
             for (uint32_t j = lane; j < D; j += 32) {
                 const K k = hkeys[list[j]];
                 const uint32_t tgt = AK::tgt(k, wb);
-                bool taken = false;
-                for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
+                bool taken = (tgt == last);
+                for (uint32_t i = 0; i + 1 < c; ++i) taken |= (chosen[i] == tgt);
                 const uint32_t cj = hits[j];
                 if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
             }
@@ -393,10 +441,13 @@ query_fast_kernel (QueryArgs a, uint32_t T)
             top[c] = mcb200_candidate{wt, wmax, beg, ww};
             chosen[c] = wt;
         }
+        last = wt;
         __syncwarp();
     }
     if (lane == 0) write_empty(top, c, a.maxc);
     warp_stats(a, true, H, nfeat, sectors);
+    __syncwarp();
+    }
 }
 
 template <bool kTax>
@@ -608,7 +659,7 @@ query_warp_kernel (QueryArgs a, uint32_t T)
     warp_stats(a, fused, H, nfeat, sectors);
 }
 
-void launch_query_warp (const QueryArgs& a, uint32_t T, int, cudaStream_t st)
+void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st)
 {
     if (!a.nq) return;
     static bool attr_set = false;
@@ -622,10 +673,14 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int, cudaStream_t st)
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
     if (!a.tax_of_tgt && !a.allhits) {
         // top hits only at rank "sequence": the sort-free kernel
-        if (a.table.win_bits)
-            query_fast_kernel<uint32_t><<<grid, kQWarps * 32, fast_smem_bytes<uint32_t>(T) * kQWarps, st>>>(a, T);
-        else
-            query_fast_kernel<uint64_t><<<grid, kQWarps * 32, fast_smem_bytes<uint64_t>(T) * kQWarps, st>>>(a, T);
+        const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(T) : fast_smem_bytes<uint64_t>(T)) * kQWarps;
+        int per_sm = 0;
+        if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t>, kQWarps * 32, smem);
+        else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t>, kQWarps * 32, smem);
+        if (per_sm < 1) per_sm = 1;
+        const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
+        if (a.table.win_bits) query_fast_kernel<uint32_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);
+        else                  query_fast_kernel<uint64_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);
     } else {
         const size_t smem = warp_smem_bytes(T) * kQWarps;
         if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T);

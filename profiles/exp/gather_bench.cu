@@ -3,6 +3,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_bench gather_bench.cu && ./gather_bench
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint64_t mix (uint64_t x) {
@@ -81,13 +82,19 @@ template <int BYTES> void run (const uint4* buf, uint64_t bytes, uint32_t* out)
     printf("granule %4d B: %8.2f G lookups/s  %8.1f GB/s useful  (%.3f ms)\n", BYTES, n / ms / 1e6, n * BYTES / ms / 1e6, ms);
 }
 
-int main ()
+int main (int argc, char** argv)
 {
-    const uint64_t maxbytes = 64ull << 30;
+    if (argc > 1) {
+        size_t g = size_t(atoi(argv[1])), back = 0;
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+        cudaDeviceGetLimit(&back, cudaLimitMaxL2FetchGranularity);
+        printf("set L2 fetch granularity %zu -> %s, reads back %zu\n", g, cudaGetErrorString(e), back);
+    }
+    const uint64_t maxbytes = 16ull << 30;
     uint4* buf; uint32_t* out;
     cudaMalloc(&buf, maxbytes); cudaMalloc(&out, 4);
     cudaMemset(buf, 1, maxbytes);
-    for (uint64_t bytes = 8ull << 30; bytes <= maxbytes; bytes *= 8) {
+    for (uint64_t bytes = 16ull << 30; bytes <= (16ull << 30); bytes *= 8) {
         printf("--- working set %.1f GB\n", bytes / 1073741824.0);
         run<16>(buf, bytes, out); run<32>(buf, bytes, out); run<64>(buf, bytes, out); run<128>(buf, bytes, out);
         run_coop<32>(buf, bytes, out); run_coop<64>(buf, bytes, out); run_coop<128>(buf, bytes, out); run_coop<256>(buf, bytes, out);
