@@ -25,6 +25,7 @@
 // (hits desc, arrival = target asc) of insert().
 #include "internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace mcb {
 
@@ -678,6 +679,8 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream
         if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t>, kQWarps * 32, smem);
         else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t>, kQWarps * 32, smem);
         if (per_sm < 1) per_sm = 1;
+        static const int cap = [] { const char* e = getenv("MCB200_QUERY_CTAS"); return e ? atoi(e) : 0; }();
+        if (cap >= 1 && cap < per_sm) per_sm = cap;
         const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
         if (a.table.win_bits) query_fast_kernel<uint32_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);
         else                  query_fast_kernel<uint64_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);

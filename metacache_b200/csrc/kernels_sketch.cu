@@ -11,6 +11,7 @@
 // and the packed bases are staged into shared memory with 1-D bulk async
 // copies (TMA engine) one tile ahead of the math.
 #include "internal.h"
+#include <cstdlib>
 
 namespace mcb {
 
@@ -311,7 +312,8 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
         cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const int grid = sm_count * 8;
+    static const int ctas_per_sm = [] { const char* e = getenv("MCB200_SKETCH_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
+    const int grid = sm_count * ctas_per_sm;
     sketch_kernel<<<grid, kSketchThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
                                                       d_nwin, p, feats, tile_windows, stage_bases);
     count_launch();
