@@ -229,6 +229,37 @@ sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ 
             const WinDesc d = s_desc[cur * tile_windows + i];
             const uint32_t nk = (d.n >= p.k) ? (d.n - p.k + 1) : 0u;
             const uint32_t s_eff = min(p.s, nk);
+            if (nk <= 32) {
+                // short window (trailing windows, short reads): one k-mer per lane, one 32-wide
+                // register sort, keep the first s_eff distinct values
+                uint32_t v = kNoFeature;
+                if (lane < nk) {
+                    const uint32_t rel = d.start + lane - base;
+                    const uint32_t wi = rel >> 4, o = rel & 15u;
+                    const uint32_t x = __funnelshift_l(sc[wi + 1], sc[wi], 2 * o);
+                    const uint32_t ai = rel >> 5, ao = rel & 31u;
+                    const uint32_t A = __funnelshift_l(sa[ai + 1], sa[ai], ao);
+                    if ((A >> (32u - p.k)) == 0) v = hash32(canonical32(x >> kshift, p.k));
+                }
+                #pragma unroll
+                for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
+                    #pragma unroll
+                    for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                        const uint32_t other = __shfl_xor_sync(kFull, v, j);
+                        const bool take_min = (((lane & k2) == 0) == ((lane & j) == 0));
+                        v = take_min ? min(v, other) : max(v, other);
+                    }
+                }
+                const uint32_t prev = __shfl_up_sync(kFull, v, 1);
+                const bool keep = (v != kNoFeature) && (lane == 0 || v != prev);
+                const uint32_t km = __ballot_sync(kFull, keep);
+                const uint32_t pos = __popc(km & ((1u << lane) - 1u));
+                const uint32_t nkeep = min(uint32_t(__popc(km)), s_eff);
+                uint32_t* dst = feats + uint64_t(w0 + i) * p.s;
+                if (keep && pos < s_eff) dst[pos] = v;
+                if (lane < p.s && lane >= nkeep) dst[lane] = kNoFeature;
+                continue;
+            }
             uint32_t run = kNoFeature;
             for (uint32_t q0 = 0; q0 < nk; q0 += 128) {
                 const uint32_t q   = q0 + 4 * lane;          // first k-mer of this lane
