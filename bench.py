@@ -234,6 +234,8 @@ def main():
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
+        if world > 1:
+            config["reference_db"] = "part 0 only (1/%d of the sharded database)" % world
         base = export_reference_db(args, db, wins, 0)
         sample = args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads)))
         reads_np = reads[:sample].cpu().numpy()
@@ -337,9 +339,18 @@ def main():
     alg_bytes = 4 * SK["sketchlen"] * nwin_launch + 16 * feats_probed + 8 * locs + 16 * MAXC * nq + 8 * nq
     k_ms = (stage[3] + stage[4]) / n_launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "query_warp_kernel (+ query_heavy_kernel) - fused probe/sort/top-hits",
+    # DRAM bytes per read of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/traffic.json; measured on a 1 M-read launch of the same workload), scaled to this launch
+    traffic = None
+    try:
+        cal = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if world == 1:
+            traffic = int(cal["query_fast_kernel"]["dram_bytes_per_read"] * nq)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "query_fast_kernel (+ query_heavy_kernel): fused probe / aggregate / top-hits",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "alg_bytes_per_launch": int(alg_bytes), "kernel_ms_per_launch": round(k_ms, 3),
                 "per_read": {"features": round(feats_probed / nq, 2), "locations": round(locs / nq, 2),
                              "table_sectors_32B": round(sectors / nq, 2)},

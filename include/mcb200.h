@@ -57,6 +57,13 @@ typedef struct mcb200_candidate {
     uint32_t tgt, hits, beg, end;
 } mcb200_candidate;
 
+/* result of classify() (classification.cpp:146-189): taxon = ordinal + 1 of the
+ * classified taxon in the lineage table handed to mcb200_db_set_target_lineages
+ * (0 = unclassified), rank = its taxonomic rank index (taxonomy.hpp:67-90).    */
+typedef struct mcb200_classification {
+    uint32_t taxon, rank;
+} mcb200_classification;
+
 typedef struct mcb200_db    mcb200_db;
 typedef struct mcb200_batch mcb200_batch;
 
@@ -100,6 +107,11 @@ int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const char* path,
  * `-lowest` rank (0 = no ancestor at that rank: candidate dropped,
  * candidate_generation.hpp:184-191).  NULL/0 restores rank "sequence".       */
 int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax_of_target, uint32_t n_targets);
+
+/* ranked lineages of all targets (taxonomy::ranked_lineage, taxonomy.hpp:368,
+ * 576-597): lineages[n_targets][21], entry = taxon ordinal + 1 at that rank, 0 =
+ * none.  Needed by the classification entry points (row N3).                  */
+int mcb200_db_set_target_lineages (mcb200_db* db, const uint32_t* lineages, uint32_t n_targets);
 
 uint32_t mcb200_db_part_count   (const mcb200_db* db);               /* table_count()  */
 uint64_t mcb200_db_key_count    (const mcb200_db* db, uint32_t part); /* key_count()    */
@@ -173,6 +185,11 @@ const mcb200_candidate* mcb200_batch_top_candidates (const mcb200_batch* b, uint
  * NULL/0 unless the batch was created with copy_all_hits.                    */
 const uint64_t* mcb200_batch_allhits (const mcb200_batch* b, uint32_t slot, uint32_t query,
                                       uint64_t* n);
+/* classification of every query of a batch: enable before submit (hits_min 0
+ * disables); results after wait: num_queries entries                          */
+int mcb200_batch_enable_classification (mcb200_batch* b, uint32_t hits_min, float hits_diff_fraction,
+                                        uint32_t lowest_rank, uint32_t highest_rank);
+const mcb200_classification* mcb200_batch_classifications (const mcb200_batch* b, uint32_t slot);
 /* per-window sketches of the last submit (for stage-level parity tests):
  * window w of the slot (windows of query i are contiguous, mate 1 first);
  * returns pointer to `sketchlen` features, *n = valid count, ascending.      */
@@ -234,6 +251,14 @@ int mcb200_merge_candidates_device (mcb200_workspace* ws, const mcb200_candidate
  * merge -> d_top.                                                            */
 int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
                          const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream);
+
+/* classify() on the device for n_queries candidate lists (d_top as produced by
+ * the query entry points): LCA over the ranked lineages of the candidates whose
+ * hits exceed (hits0 - hits_min) * hits_diff_fraction; lowest_rank = the rank
+ * candidates were generated at, highest_rank = `-highest` (options.hpp:245-258) */
+int mcb200_classify_device (mcb200_workspace* ws, const mcb200_candidate* d_top, uint32_t n_queries,
+                            uint32_t hits_min, float hits_diff_fraction, uint32_t lowest_rank,
+                            uint32_t highest_rank, mcb200_classification* d_out, void* stream);
 
 /* workspace introspection (device pointers, valid after the calls above)     */
 uint32_t        mcb200_workspace_num_windows   (const mcb200_workspace* ws);   /* syncs */

@@ -33,6 +33,10 @@ class Candidate(C.Structure):
     _fields_ = [("tgt", C.c_uint32), ("hits", C.c_uint32), ("beg", C.c_uint32), ("end", C.c_uint32)]
 
 
+class Classification(C.Structure):
+    _fields_ = [("taxon", C.c_uint32), ("rank", C.c_uint32)]
+
+
 class DevQueries(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("seq_offsets", C.c_void_p), ("seq_query", C.c_void_p),
                 ("max_win", C.c_void_p), ("n_seqs", C.c_uint32), ("n_queries", C.c_uint32),
@@ -72,6 +76,10 @@ _SIGS = {
     "mcb200_db_part_finish": (C.c_int, [_P, C.c_uint32]),
     "mcb200_db_load_cache_file": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_float]),
     "mcb200_db_set_target_taxa": (C.c_int, [_P, _P, C.c_uint32]),
+    "mcb200_db_set_target_lineages": (C.c_int, [_P, _P, C.c_uint32]),
+    "mcb200_classify_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, _P, _P]),
+    "mcb200_batch_enable_classification": (C.c_int, [_P, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32]),
+    "mcb200_batch_classifications": (C.POINTER(Classification), [_P, C.c_uint32]),
     "mcb200_db_part_count": (C.c_uint32, [_P]),
     "mcb200_db_key_count": (C.c_uint64, [_P, C.c_uint32]),
     "mcb200_db_value_count": (C.c_uint64, [_P, C.c_uint32]),

@@ -89,6 +89,8 @@ struct mcb200_db {
     std::vector<Part> parts;
     uint64_t* d_tax = nullptr;
     uint32_t  n_tax = 0;
+    uint32_t* d_lineages = nullptr;          // [n_lin][21]
+    uint32_t  n_lin = 0;
     int*      d_error = nullptr;
     cudaStream_t stream = nullptr;
     // staging for host appends
@@ -147,6 +149,7 @@ extern "C" void mcb200_db_close (mcb200_db* db) {
     cudaSetDevice(db->device);
     for (auto& p : db->parts) free_part(p);
     if (db->d_tax) cudaFree(db->d_tax);
+    if (db->d_lineages) cudaFree(db->d_lineages);
     if (db->d_error) cudaFree(db->d_error);
     db->st_keys.release(); db->st_sizes.release(); db->st_off.release();
     if (db->scan_tmp) cudaFree(db->scan_tmp);
@@ -289,6 +292,17 @@ extern "C" int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax, ui
     CU(cudaMalloc(&db->d_tax, uint64_t(n) * 8));
     CU(cudaMemcpy(db->d_tax, tax, uint64_t(n) * 8, cudaMemcpyHostToDevice));
     db->n_tax = n;
+    return 0;
+}
+
+extern "C" int mcb200_db_set_target_lineages (mcb200_db* db, const uint32_t* lin, uint32_t n) {
+    if (!db) return fail(MCB200_EINVAL, "null database handle");
+    CU(cudaSetDevice(db->device));
+    if (db->d_lineages) { cudaFree(db->d_lineages); db->d_lineages = nullptr; db->n_lin = 0; }
+    if (!lin || !n) return 0;
+    CU(cudaMalloc(&db->d_lineages, uint64_t(n) * 21 * 4));
+    CU(cudaMemcpy(db->d_lineages, lin, uint64_t(n) * 21 * 4, cudaMemcpyHostToDevice));
+    db->n_lin = n;
     return 0;
 }
 
@@ -695,6 +709,19 @@ extern "C" int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_
     return 0;
 }
 
+extern "C" int mcb200_classify_device (mcb200_workspace* ws, const mcb200_candidate* d_top, uint32_t n_queries,
+                                       uint32_t hits_min, float frac, uint32_t lowest, uint32_t highest,
+                                       mcb200_classification* d_out, void* stream) {
+    if (!ws || !d_top || !d_out) return fail(MCB200_EINVAL, "null argument");
+    if (!ws->db->d_lineages) return fail(MCB200_ESTATE, "mcb200_db_set_target_lineages must be called first");
+    if (lowest > 20 || highest > 20) return fail(MCB200_EINVAL, "rank out of range");
+    CU(cudaSetDevice(ws->db->device));
+    launch_classify(d_top, n_queries, ws->maxc, ws->db->d_lineages, ws->db->n_lin, hits_min, frac, lowest, highest,
+                    d_out, static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" uint32_t mcb200_workspace_num_windows (const mcb200_workspace* ws) {
     if (!ws || !ws->sketched || ws->q.n_queries == 0) return 0;
     cudaSetDevice(ws->db->device);
@@ -859,6 +886,7 @@ struct Slot_ {
     PinBuf<char> h_bases; PinBuf<uint32_t> h_seq_off, h_seq_query, h_max_win;
     DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off, d_seq_query, d_max_win;
     DevBuf<mcb200_candidate> d_top; PinBuf<mcb200_candidate> h_top;
+    DevBuf<mcb200_classification> d_cls; PinBuf<mcb200_classification> h_cls; bool has_cls = false;
     PinBuf<uint32_t> h_feats, h_qry_win_off; PinBuf<uint64_t> h_allhits, h_allhits_off;
     uint32_t n_queries = 0, n_seqs = 0, n_windows = 0; uint64_t n_bases = 0;
     uint32_t sub_queries = 0, sub_s = 0;
@@ -870,6 +898,7 @@ struct Slot_ {
 };
 
 struct mcb200_batch {
+    uint32_t cls_hits_min = 0, cls_lowest = 0, cls_highest = 19; float cls_frac = 1.0f;
     mcb200_db* db = nullptr;
     uint32_t max_queries = 0, maxc = 2; uint64_t max_bases = 0; bool allhits = false;
     std::vector<Slot_> slots;
@@ -917,6 +946,7 @@ extern "C" void mcb200_batch_destroy (mcb200_batch* b) {
         s.h_bases.release(); s.h_seq_off.release(); s.h_seq_query.release(); s.h_max_win.release();
         s.d_bases.release(); s.d_seq_off.release(); s.d_seq_query.release(); s.d_max_win.release();
         s.d_top.release(); s.h_top.release(); s.h_feats.release(); s.h_qry_win_off.release();
+        s.d_cls.release(); s.h_cls.release();
         s.h_allhits.release(); s.h_allhits_off.release();
         if (s.ws) mcb200_workspace_destroy(s.ws);
         if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -1009,7 +1039,17 @@ extern "C" int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200
     mcb200_dev_queries q{s.d_bases.p, s.d_seq_off.p, s.d_seq_query.p, s.d_max_win.p, s.n_seqs, s.n_queries, s.n_bases};
     rc = mcb200_query_device(s.ws, &q, sk, s.d_top.p, st);
     if (rc) return rc;
+    s.has_cls = false;
+    if (b->cls_hits_min > 0 && b->db->d_lineages) {
+        CU(s.d_cls.ensure(b->max_queries)); CU(s.h_cls.ensure(b->max_queries));
+        rc = mcb200_classify_device(s.ws, s.d_top.p, s.n_queries, b->cls_hits_min, b->cls_frac, b->cls_lowest,
+                                    b->cls_highest, s.d_cls.p, st);
+        if (rc) return rc;
+        s.has_cls = true;
+    }
     CU(cudaEventRecord(s.ev_k1, st));
+    if (s.has_cls) CU(cudaMemcpyAsync(s.h_cls.p, s.d_cls.p, uint64_t(s.n_queries) * sizeof(mcb200_classification),
+                                      cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s.h_top.p, s.d_top.p, uint64_t(s.n_queries) * b->maxc * sizeof(mcb200_candidate),
                        cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev_done, st));
@@ -1133,6 +1173,20 @@ extern "C" uint32_t mcb200_batch_query_window_offset (const mcb200_batch* b, uin
     const Slot_& s = b->slots[slot];
     if (query > s.sub_queries) return s.n_windows;
     return s.h_qry_win_off.p[query];
+}
+
+extern "C" int mcb200_batch_enable_classification (mcb200_batch* b, uint32_t hits_min, float frac,
+                                                   uint32_t lowest, uint32_t highest) {
+    if (!b) return fail(MCB200_EINVAL, "null batch handle");
+    if (lowest > 20 || highest > 20) return fail(MCB200_EINVAL, "rank out of range");
+    b->cls_hits_min = hits_min; b->cls_frac = frac; b->cls_lowest = lowest; b->cls_highest = highest;
+    return 0;
+}
+
+extern "C" const mcb200_classification* mcb200_batch_classifications (const mcb200_batch* b, uint32_t slot) {
+    if (!b || slot >= b->slots.size()) return nullptr;
+    const Slot_& s = b->slots[slot];
+    return (s.waited && s.has_cls) ? s.h_cls.p : nullptr;
 }
 
 extern "C" int mcb200_batch_span_ms (const mcb200_batch* b, uint32_t first_slot, uint32_t n_slots, float* ms) {

@@ -84,4 +84,8 @@ void launch_merge_candidates (const mcb200_candidate* parts, uint32_t n_lists, u
                               uint32_t maxc, const uint64_t* tax_of_tgt, uint32_t n_tax,
                               mcb200_candidate* out, cudaStream_t st);
 
+void launch_classify (const mcb200_candidate* top, uint32_t nq, uint32_t maxc, const uint32_t* lineages,
+                      uint32_t n_targets, uint32_t hits_min, float frac, uint32_t lowest, uint32_t highest,
+                      mcb200_classification* out, cudaStream_t st);
+
 } // namespace mcb

@@ -955,6 +955,54 @@ __global__ void merge_candidates_kernel (const mcb200_candidate* __restrict__ pa
     write_empty(dst, ntop, maxc);
 }
 
+// ---------------------------------------------------------------------------
+// classify(): ranked LCA of the candidates above the hit threshold
+// (classification.cpp:146-189, taxonomy.hpp:1291-1301); one thread per read
+// ---------------------------------------------------------------------------
+__global__ void classify_kernel (const mcb200_candidate* __restrict__ top, uint32_t nq, uint32_t maxc,
+                                 const uint32_t* __restrict__ lineages, uint32_t n_targets,
+                                 uint32_t hits_min, float frac, uint32_t lowest, uint32_t highest,
+                                 mcb200_classification* __restrict__ out)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const mcb200_candidate* c = top + uint64_t(q) * maxc;
+    mcb200_classification res{0u, 21u};
+    const mcb200_candidate c0 = c[0];
+    if (c0.hits != 0 && c0.tgt < n_targets && c0.hits >= hits_min) {
+        const uint32_t* lin0 = lineages + uint64_t(c0.tgt) * 21;
+        uint32_t r = lowest;
+        while (r < 21 && !lin0[r]) ++r;
+        if (r < 21) {
+            const float threshold = c0.hits > hits_min ? __fmul_rn(float(c0.hits - hits_min), frac) : 0.0f;
+            uint32_t lca = lin0[r];
+            bool ok = true;
+            for (uint32_t i = 1; i < maxc && ok; ++i) {
+                const mcb200_candidate ci = c[i];
+                if (ci.hits == 0 || !(float(ci.hits) > threshold)) break;
+                if (ci.tgt >= n_targets) { ok = false; break; }
+                const uint32_t* lin = lineages + uint64_t(ci.tgt) * 21;
+                uint32_t x = r;
+                while (x <= 20 && !(lin0[x] && lin0[x] == lin[x])) ++x;
+                if (x > 20 || x > highest) { ok = false; break; }
+                r = x; lca = lin0[x];
+            }
+            if (ok && r <= highest) { res.taxon = lca; res.rank = r; }
+        }
+    }
+    out[q] = res;
+}
+
+void launch_classify (const mcb200_candidate* top, uint32_t nq, uint32_t maxc, const uint32_t* lineages,
+                      uint32_t n_targets, uint32_t hits_min, float frac, uint32_t lowest, uint32_t highest,
+                      mcb200_classification* out, cudaStream_t st)
+{
+    if (!nq) return;
+    classify_kernel<<<(nq + 255) / 256, 256, 0, st>>>(top, nq, maxc, lineages, n_targets, hits_min, frac, lowest,
+                                                      highest, out);
+    count_launch();
+}
+
 void launch_merge_candidates (const mcb200_candidate* parts, uint32_t n_lists, uint32_t nq,
                               uint32_t maxc, const uint64_t* tax_of_tgt, uint32_t n_tax,
                               mcb200_candidate* out, cudaStream_t st)

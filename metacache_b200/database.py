@@ -191,6 +191,42 @@ class Database:
                     break
         return keys
 
+    # -- ranked lineages (taxonomy.hpp:368, 576-597) for classify() ---------------------
+    def target_lineages(self) -> np.ndarray:
+        """[n_targets, 21] u32: taxon ordinal + 1 (index into meta.taxa) at every rank, 0 = none;
+        `taxonomy::ranked_lineage` of each target as make_ranks builds it."""
+        m = self.meta
+        ordinal = {t.id: i + 1 for i, t in enumerate(m.taxa)}
+        by_id = {t.id: t for t in m.taxa}
+        lin = np.zeros((m.target_count, RANK_NONE), dtype=np.uint32)
+        for t in m.taxa:
+            if t.id >= 0:
+                continue
+            tgt = -t.id - 1
+            if tgt >= m.target_count:
+                continue
+            if t.rank != RANK_NONE:
+                lin[tgt, t.rank] = ordinal[t.id]
+            pid = t.parent
+            while pid != 0:
+                a = by_id.get(pid)
+                if a is None or a.id < 0:
+                    break
+                if a.rank != RANK_NONE:
+                    lin[tgt, a.rank] = ordinal[a.id]
+                if a.parent == pid:
+                    break
+                pid = a.parent
+        return lin
+
+    def copy_target_lineages_to_gpus(self, lineages: Optional[np.ndarray] = None):
+        """gpu_hashmap::copy_target_lineages_to_gpus: ranked lineages for on-device classify()"""
+        if lineages is None:
+            lineages = self.target_lineages()
+        lineages = np.ascontiguousarray(lineages, dtype=np.uint32)
+        check(lib().mcb200_db_set_target_lineages(self._h, lineages.ctypes.data, lineages.shape[0]))
+        self._lineages = lineages
+
     def set_lowest_rank(self, lowest_rank: int):
         """copy_target_lineages_to_gpus + the `lowestRank` argument of query_gpu_async."""
         if lowest_rank == self._lowest_rank:
@@ -274,6 +310,14 @@ class QueryHostData:
             out.append(np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32))
         return out
 
+    def classifications(self) -> np.ndarray:
+        """[num_queries, 2] u32 (taxon ordinal + 1 or 0, rank) after wait_for_results, if enabled"""
+        n = self.num_queries()
+        p = lib().mcb200_batch_classifications(self._b._h, self._id)
+        if not p or n == 0:
+            return np.zeros((0, 2), np.uint32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n, 2)).copy()
+
     def last_timing(self):
         t, k = C.c_float(0), C.c_float(0)
         check(lib().mcb200_batch_last_timing(self._b._h, self._id, C.byref(t), C.byref(k)))
@@ -306,6 +350,13 @@ class QueryBatch:
         except Exception:
             pass
 
+    def enable_classification(self, hits_min: int, hits_diff_fraction: float = 1.0,
+                              lowest_rank: int = RANK_SEQUENCE, highest_rank: int = 19):
+        """classify() (classification.cpp:146-189) on the device for every query of a submit;
+        hitsMin default = sketchlen/3 (querying.cpp:256-260), highest default = domain"""
+        check(lib().mcb200_batch_enable_classification(self._h, hits_min, hits_diff_fraction, lowest_rank,
+                                                       highest_rank))
+
     def host_data(self, host_id: int) -> QueryHostData:
         return self._hosts[host_id]
 
@@ -333,15 +384,25 @@ class QueryBatch:
                                                   nq, int(paired), insert_size_max, winstride))
 
 
+def default_hits_min(sketchlen: int) -> int:
+    """querying.cpp:256-263"""
+    if sketchlen >= 6:
+        return int(sketchlen / 3.0)
+    return 2 if sketchlen >= 4 else 1
+
+
 def query_reads(db: Database, reads: Sequence, sketching: Optional[SketchingOpt] = None,
                 max_candidates: int = 2, insert_size_max: int = 0, copy_all_hits: bool = True,
-                lowest_rank: int = RANK_SEQUENCE, batch_queries: int = 8192, with_sketches: bool = False):
+                lowest_rank: int = RANK_SEQUENCE, batch_queries: int = 8192, with_sketches: bool = False,
+                classify: bool = False, hits_diff_fraction: float = 1.0, highest_rank: int = 19):
     """query_gpu (database_query.hpp:87-124) for a list of reads (bytes or (bytes, bytes)):
     fills batches, submits, waits, collects (allhits, top candidates[, sketches]) per read."""
     sk = sketching or db.target_sketching()
     pairs = [(r, b"") if isinstance(r, (bytes, bytearray)) else (r[0], r[1]) for r in reads]
     max_bases = max(1 << 20, 2 * max((len(a) + len(b) for a, b in pairs), default=0))
     qb = QueryBatch(db, batch_queries, max_bases, max_candidates, copy_all_hits, 1)
+    if classify:
+        qb.enable_classification(default_hits_min(sk.sketchlen), hits_diff_fraction, lowest_rank, highest_rank)
     hd = qb.host_data(0)
     results = []
 
@@ -350,11 +411,14 @@ def query_reads(db: Database, reads: Sequence, sketching: Optional[SketchingOpt]
             return
         db.query_gpu_async(qb, 0, sk, lowest_rank)
         hd.wait_for_results()
+        cls = hd.classifications() if classify else None
         for s in range(hd.num_queries()):
             top = [c.as_tuple() for c in hd.top_candidates(s) if c.hits > 0]
             item = [hd.allhits(s) if copy_all_hits else None, top]
             if with_sketches:
                 item.append(hd.sketches(s))
+            if classify:
+                item.append((int(cls[s, 0]), int(cls[s, 1])))
             results.append(tuple(item))
         hd.clear()
 

@@ -30,3 +30,16 @@ def format_top_hits(top, target_names: Sequence[str]) -> str:
             break
         out.append(f"{target_names[tgt]}:{hits}")
     return ",".join(out)
+
+
+RANK_NAMES = ["sequence", "form", "variety", "subspecies", "species", "subgenus", "genus", "subtribe", "tribe",
+              "subfamily", "family", "suborder", "order", "subclass", "class", "subphylum", "phylum",
+              "subkingdom", "kingdom", "domain", "root", "none"]          # taxonomy.hpp:226-252
+
+
+def format_classification(taxon_ordinal: int, rank: int, taxa) -> str:
+    """show_taxon (printing.cpp:250-280) in its default style: `rank:name`, `--` if unclassified.
+    taxon_ordinal = index + 1 into `taxa` (DbMeta.taxa), 0 = unclassified."""
+    if taxon_ordinal == 0:
+        return "--"
+    return f"{RANK_NAMES[rank]}:{taxa[taxon_ordinal - 1].name}"

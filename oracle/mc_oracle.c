@@ -396,6 +396,42 @@ uint32_t mco_merge_tops (const mco_candidate* parts_top, const uint32_t* parts_n
     return ntop;
 }
 
+/* ---------------------------------------------------------------------------
+ * classification.cpp:146-189  classify(): LCA over the ranked lineages of the
+ * candidates whose hits exceed (hits0 - hitsMin) * hitsDiffFraction (float).
+ * taxonomy.hpp:1291-1301 ranked_lca: first rank >= lowest where both lineages
+ * hold the same non-null taxon.  lineages: [n_targets][21], taxon ordinal + 1,
+ * 0 = none (taxonomy.hpp:576-597 make_ranks; index = rank).  `lowest` is the
+ * rank candidates were generated at (cand.tax = lowest_ranked_ancestor).
+ * Returns taxon ordinal + 1 (0 = unclassified); *rank_out = its rank.          */
+uint32_t mco_classify (const mco_candidate* top, uint32_t ntop, const uint32_t* lineages,
+                       uint32_t n_targets, uint32_t hits_min, float hits_diff_fraction,
+                       uint32_t lowest, uint32_t highest, uint32_t* rank_out)
+{
+    if (rank_out) *rank_out = 21;
+    if (ntop == 0 || top[0].tgt >= n_targets) return 0;
+    const uint32_t* lin0 = lineages + (uint64_t)top[0].tgt * 21;
+    uint32_t r = lowest;
+    while (r < 21 && !lin0[r]) ++r;                     /* cand[0].tax */
+    if (r >= 21) return 0;
+    if (top[0].hits < hits_min) return 0;
+    uint32_t lca = lin0[r];
+    const float threshold = top[0].hits > hits_min ? (float)(top[0].hits - hits_min) * hits_diff_fraction : 0.0f;
+    for (uint32_t i = 1; i < ntop; ++i) {
+        if (!((float)top[i].hits > threshold)) break;
+        if (top[i].tgt >= n_targets) return 0;
+        const uint32_t* lin = lineages + (uint64_t)top[i].tgt * 21;
+        uint32_t x = r;
+        while (x <= 20 && !(lin0[x] && lin0[x] == lin[x])) ++x;
+        if (x > 20) return 0;
+        r = x; lca = lin0[x];
+        if (r > highest) return 0;
+    }
+    if (r > highest) return 0;
+    if (rank_out) *rank_out = r;
+    return lca;
+}
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ def lib():
                                 C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
         L.mco_merge_tops.restype = C.c_uint32
         L.mco_merge_tops.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.mco_classify.restype = C.c_uint32
+        L.mco_classify.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float,
+                                   C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -167,3 +170,14 @@ def merge_tops(parts_tops, maxc=2):
     top = (Candidate * max(maxc, 1))()
     n = lib().mco_merge_tops(buf, cnt.ctypes.data, nparts, maxc, top)
     return [(top[i].tgt, top[i].hits, top[i].beg, top[i].end) for i in range(n)]
+
+
+def classify(top, lineages, hits_min=5, hits_diff_fraction=1.0, lowest=0, highest=19):
+    """top: [(tgt, hits, beg, end)...]; lineages: np.uint32 [n_targets, 21] (taxon ordinal + 1).
+    -> (taxon ordinal + 1 or 0, rank)"""
+    lineages = np.ascontiguousarray(lineages, dtype=np.uint32)
+    buf = (Candidate * max(len(top), 1))(*[Candidate(*t) for t in top])
+    rank = C.c_uint32(21)
+    t = lib().mco_classify(buf, len(top), lineages.ctypes.data, lineages.shape[0], hits_min, hits_diff_fraction,
+                           lowest, highest, C.byref(rank))
+    return t, rank.value

@@ -211,7 +211,8 @@ def test_c1_bundled_database_matches_reference_golden_file():
             continue
         cols = line.rstrip("\n").split("\t|\t")
         if len(cols) == 6 and cols[0].isdigit():
-            expected.setdefault(section, {})[int(cols[0])] = (cols[3], cols[4])   # by query id
+            expected.setdefault(section, {})[int(cols[0])] = (cols[3], cols[4], cols[5])   # by query id
+    db.copy_target_lineages_to_gpus()
     single = refio.read_fasta(os.path.join(C1, "single.fa"))
     pf = refio.read_fasta(os.path.join(C1, "pairs.fa"))
     p1 = refio.read_fasta(os.path.join(C1, "pair.1.fa"))
@@ -221,18 +222,21 @@ def test_c1_bundled_database_matches_reference_golden_file():
         "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)],
         "pair.1 + data/pair.2": [(a[1], b[1]) for a, b in zip(p1, p2)],
     }
-    total = 0
+    total = classified = 0
     for sec, items in runs.items():
         exp = expected[sec]
-        res = query_reads(db, items, copy_all_hits=True)
-        for qid, (allh, top) in enumerate(res, start=1):
+        res = query_reads(db, items, copy_all_hits=True, classify=True)
+        for qid, (allh, top, cls) in enumerate(res, start=1):
             if qid not in exp:
                 continue
             assert formatting.format_all_hits(allh, names) == exp[qid][0], (sec, qid)
             want = exp[qid][1] if exp[qid][1] != "--" else ""
             assert formatting.format_top_hits(top, names) == want, (sec, qid)
+            # classification column (classify(): LCA of the candidates above the hit threshold)
+            assert formatting.format_classification(cls[0], cls[1], db.meta.taxa) == exp[qid][2], (sec, qid)
             total += 1
-    assert total > 30000
+            classified += cls[0] != 0
+    assert total > 30000 and classified > 150
     db.close()
 
 
@@ -349,3 +353,36 @@ def test_export_round_trip_packed_layout(g1):
     roffs = np.zeros(len(g1.sizes) + 1, np.int64); np.cumsum(g1.sizes, out=roffs[1:])
     for a, b in zip(o, ro):
         assert np.array_equal(v[offs[a]:offs[a + 1]], g1.values[roffs[b]:roffs[b + 1]])
+
+
+def test_classify_on_device_matches_oracle_with_synthetic_lineages(g1):
+    """classify() with a made-up taxonomy over the golden targets: exercises LCA at several ranks,
+    the hit-difference threshold and the highest-rank cut-off"""
+    from metacache_b200.database import query_reads
+    from oracle import mc_oracle as O
+    nt = len(g1.target_windows)
+    lin = np.zeros((nt, 21), np.uint32)
+    for t in range(nt):
+        lin[t, 0] = 1 + t                        # sequence level: the target itself
+        fam = {10: 0, 11: 0, 12: 3, 13: 3, 14: 7, 15: 7}.get(t, t)
+        lin[t, 4] = 100 + fam                    # species: G0/G0m1/G0m2 share one, ...
+        if t % 3:
+            lin[t, 6] = 200 + fam // 4           # genus missing for every third target
+        lin[t, 16] = 300 + (fam % 2)             # phylum
+        lin[t, 19] = 400                         # domain
+    g1.db.copy_target_lineages_to_gpus(lin)
+    tab = O.Table(g1.keys, g1.sizes, g1.values)
+    for frac, highest, maxc in ((1.0, 19, 2), (0.3, 19, 4), (1.0, 6, 4), (0.0, 16, 5)):
+        res = query_reads(g1.db, g1.reads, _sk(g1), max_candidates=maxc, copy_all_hits=False, classify=True,
+                          hits_diff_fraction=frac, highest_rank=highest)
+        n_cls = 0
+        for i, (a, b) in enumerate(g1.reads):
+            _, top = O.query(tab, a, b, maxc=maxc)
+            want = O.classify(top, lin, hits_min=5, hits_diff_fraction=frac, lowest=0, highest=highest)
+            got = res[i][2]
+            if want[0] == 0:
+                assert got[0] == 0, (i, frac, highest)
+            else:
+                assert got == want, (i, frac, highest)
+                n_cls += 1
+        assert n_cls > 300

@@ -119,3 +119,40 @@ def test_oracle_matches_reference_golden_file():
         assert formatting.format_top_hits(top, names) == want_top, h
         checked += 1
     assert checked > 10000
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
+                    reason="oracle/_ref/c1 not built (needs /root/reference)")
+def test_oracle_classification_matches_reference_golden_file():
+    """classify() restatement vs the last column of classified.expected (all three sections)"""
+    from metacache_b200 import dbformat, formatting
+    from metacache_b200.database import Database
+    from oracle import refio
+    meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
+    c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
+    tab = O.Table(c.keys, c.sizes, c.values)
+    db = Database.__new__(Database)
+    db.meta = meta
+    lin = Database.target_lineages(db)
+    expected, section = {}, None
+    for line in open(os.path.join(C1, "classified.expected")):
+        if line.startswith("# data/"):
+            section = line.strip()[7:]
+        if line.startswith("#"):
+            continue
+        cols = line.rstrip("\n").split("\t|\t")
+        if len(cols) == 6 and cols[0].isdigit():
+            expected.setdefault(section, {})[int(cols[0])] = cols[5]
+    single = refio.read_fasta(os.path.join(C1, "single.fa"))
+    pf = refio.read_fasta(os.path.join(C1, "pairs.fa"))
+    runs = {"single": [(s, b"") for _, s in single],
+            "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)]}
+    classified = 0
+    for sec, items in runs.items():
+        for qid, (a, b) in enumerate(items, start=1):
+            _, top = O.query(tab, a, b)
+            t, r = O.classify(top, lin, hits_min=5)
+            got = formatting.format_classification(t, r, meta.taxa)
+            assert got == expected[sec][qid], (sec, qid, top)
+            classified += t != 0
+    assert classified > 150
