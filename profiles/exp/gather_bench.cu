@@ -82,6 +82,49 @@ template <int BYTES> void run (const uint4* buf, uint64_t bytes, uint32_t* out)
     printf("granule %4d B: %8.2f G lookups/s  %8.1f GB/s useful  (%.3f ms)\n", BYTES, n / ms / 1e6, n * BYTES / ms / 1e6, ms);
 }
 
+// one thread reads a granule with 256-bit loads (the table's own access pattern)
+template <int BYTES>
+__global__ void gather_v8 (const uint4* __restrict__ buf, uint64_t ngran, uint32_t iters, uint32_t* out)
+{
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    constexpr int V = BYTES / 32;
+    for (uint32_t it = 0; it < iters; it += 4) {
+        uint32_t r[4][V][8];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t g = mix(tid * 1315423911ull + it + u) % ngran;
+            #pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint4* p = buf + (g * V + v) * 2;
+                asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    : "=r"(r[u][v][0]), "=r"(r[u][v][1]), "=r"(r[u][v][2]), "=r"(r[u][v][3]),
+                      "=r"(r[u][v][4]), "=r"(r[u][v][5]), "=r"(r[u][v][6]), "=r"(r[u][v][7]) : "l"(p));
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u)
+            #pragma unroll
+            for (int v = 0; v < V; ++v)
+                #pragma unroll
+                for (int w = 0; w < 8; ++w) acc ^= r[u][v][w];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+template <int BYTES> void run_v8 (const uint4* buf, uint64_t bytes, uint32_t* out)
+{
+    const uint64_t ngran = bytes / BYTES;
+    const int blocks = 148 * 16, threads = 256; const uint32_t iters = 64;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    gather_v8<BYTES><<<blocks, threads>>>(buf, ngran, iters, out);
+    cudaEventRecord(e0);
+    for (int r = 0; r < 3; ++r) gather_v8<BYTES><<<blocks, threads>>>(buf, ngran, iters, out);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+    const double n = double(blocks) * threads * iters;
+    printf("ldg256  %4d B: %8.2f G lookups/s  %8.1f GB/s useful  (%.3f ms)\n", BYTES, n / ms / 1e6, n * BYTES / ms / 1e6, ms);
+}
+
 int main (int argc, char** argv)
 {
     if (argc > 1) {
@@ -94,9 +137,10 @@ int main (int argc, char** argv)
     uint4* buf; uint32_t* out;
     cudaMalloc(&buf, maxbytes); cudaMalloc(&out, 4);
     cudaMemset(buf, 1, maxbytes);
-    for (uint64_t bytes = 16ull << 30; bytes <= (16ull << 30); bytes *= 8) {
+    for (uint64_t bytes = 1ull << 30; bytes <= (16ull << 30); bytes *= 4) {
         printf("--- working set %.1f GB\n", bytes / 1073741824.0);
         run<16>(buf, bytes, out); run<32>(buf, bytes, out); run<64>(buf, bytes, out); run<128>(buf, bytes, out);
+        run_v8<32>(buf, bytes, out); run_v8<64>(buf, bytes, out); run_v8<128>(buf, bytes, out);
         run_coop<32>(buf, bytes, out); run_coop<64>(buf, bytes, out); run_coop<128>(buf, bytes, out); run_coop<256>(buf, bytes, out);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));

@@ -1,0 +1,21 @@
+# Round-1 evidence run (one gpurun call): GPU parity tests, both bench arms, the ncu launch list and
+# one `--set full` capture each of the two dominant kernels.  Outputs land in gpurun_out/ and are
+# turned into profiles/*_r1.* by `python profiles/collect.py r1`.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+nproc > gpurun_out/nproc.txt
+( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+( timeout 600 python bench.py --impl reference 2>&1 | tail -1 ) > gpurun_out/bench_ref.log
+( timeout 600 python bench.py 2>&1 | tail -1 ) > gpurun_out/bench_full.log
+cut -c1-600 gpurun_out/bench_ref.log; cut -c1-1500 gpurun_out/bench_full.log
+K='regex:^(encode|count_windows|fill_windows|sketch|query_fast|query_warp|query_heavy|merge_candidates|count_hits|table_insert|classify)_kernel|DeviceScan'
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$K" -c 400 --csv \
+    --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
+tail -c 200 gpurun_out/launches_bench.log
+# full captures on a 1 M-read launch of the same workload (the 4th launch of each kernel = after warm-up)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:query_fast_kernel -s 3 -c 1 -f -o gpurun_out/prof_query_r1 \
+    python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_query.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sketch_kernel -s 3 -c 1 -f -o gpurun_out/prof_sketch_r1 \
+    python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_sketch.log 2>&1
+ls -la gpurun_out
