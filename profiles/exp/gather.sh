@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 ./profiles/exp/gather_bench > gpurun_out/gather_bench.log 2>&1
 cat gpurun_out/gather_bench.log
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_requests_srcunit_tex_op_read.sum \
-   --clock-control none --csv --log-file gpurun_out/gather_ncu.csv ./profiles/exp/gather_bench > /dev/null 2>&1
+   --clock-control none -k regex:pat_ --csv --log-file gpurun_out/gather_ncu.csv ./profiles/exp/gather_bench > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
 rows = list(csv.reader(open('gpurun_out/gather_ncu.csv')))

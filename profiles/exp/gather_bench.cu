@@ -125,6 +125,107 @@ template <int BYTES> void run_v8 (const uint4* buf, uint64_t bytes, uint32_t* ou
     printf("ldg256  %4d B: %8.2f G lookups/s  %8.1f GB/s useful  (%.3f ms)\n", BYTES, n / ms / 1e6, n * BYTES / ms / 1e6, ms);
 }
 
+// ---- access patterns of candidate table layouts (bins = 128-byte lines, the DRAM fetch unit) ----
+// P1': 2 lanes x LDG.256 read one 64-byte bin           (is it one L2 request like 4 x LDG.128 ?)
+// P3 : 4 lanes x LDG.128 read the front 64 bytes; PCT % of the lookups then read the back 64 bytes (L2 hit)
+// P4 : one lane reads sector 0 (LDG.256), then PCT % read one more sector of the same line (L2 hit)
+__device__ __forceinline__ void ldg256 (const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__global__ void pat_p1 (const uint4* __restrict__ buf, uint64_t nlines64, uint32_t iters, uint32_t* out)
+{
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t grp = tid / 2; const uint32_t sub = tid % 2;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it += 4) {
+        uint32_t r[4][8];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t g = mix(grp * 1315423911ull + it + u) % nlines64;
+            ldg256(buf + g * 4 + sub * 2, r[u]);
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u)
+            #pragma unroll
+            for (int w = 0; w < 8; ++w) acc ^= r[u][w];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+template <int PCT>
+__global__ void pat_p3 (const uint4* __restrict__ buf, uint64_t nlines128, uint32_t iters, uint32_t* out)
+{
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t grp = tid / 4; const uint32_t sub = tid % 4;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it += 4) {
+        uint4 r[4]; uint64_t g[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            g[u] = mix(grp * 1315423911ull + it + u) % nlines128;
+            r[u] = __ldg(buf + g[u] * 8 + sub);
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc ^= r[u].x ^ r[u].y ^ r[u].z ^ r[u].w;
+            // data dependent second access (buffer is all 0x01010101, so the xor of r keeps the decision random via g)
+            if (((g[u] >> 7) + (r[u].x & 1u)) % 100 < PCT + 1 && PCT > 0) {
+                const uint4 s = __ldg(buf + g[u] * 8 + 4 + sub);
+                acc ^= s.x ^ s.y ^ s.z ^ s.w;
+            }
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+template <int PCT>
+__global__ void pat_p4 (const uint4* __restrict__ buf, uint64_t nlines128, uint32_t iters, uint32_t* out)
+{
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it += 4) {
+        uint32_t r[4][8]; uint64_t g[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            g[u] = mix(tid * 1315423911ull + it + u) % nlines128;
+            ldg256(buf + g[u] * 8, r[u]);
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            #pragma unroll
+            for (int w = 0; w < 8; ++w) acc ^= r[u][w];
+            if (((g[u] >> 7) + (r[u][0] & 1u)) % 100 < PCT + 1 && PCT > 0) {
+                uint32_t s[8];
+                ldg256(buf + g[u] * 8 + 2 + 2 * ((g[u] >> 3) % 3), s);
+                #pragma unroll
+                for (int w = 0; w < 8; ++w) acc ^= s[w];
+            }
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+template <class F> void run_pat (const char* name, F launch, double lookups)
+{
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch();
+    cudaEventRecord(e0);
+    for (int r = 0; r < 3; ++r) launch();
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+    printf("%-44s %8.2f G lookups/s  (%.3f ms)\n", name, lookups / ms / 1e6, ms);
+}
+void run_patterns (const uint4* buf, uint64_t bytes, uint32_t* out)
+{
+    const int blocks = 148 * 16, threads = 256; const uint32_t iters = 64;
+    const double n = double(blocks) * threads * iters;
+    run_pat("P1' 2 lanes x LDG.256, 64 B bin", [&] { pat_p1<<<blocks, threads>>>(buf, bytes / 64, iters, out); }, n / 2);
+    run_pat("P3  4x16 B front half only", [&] { pat_p3<0><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n / 4);
+    run_pat("P3  4x16 B front + 20% back half", [&] { pat_p3<20><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n / 4);
+    run_pat("P3  4x16 B front + 40% back half", [&] { pat_p3<40><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n / 4);
+    run_pat("P4  1 lane sector 0 only", [&] { pat_p4<0><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n);
+    run_pat("P4  1 lane sector 0 + 40% second sector", [&] { pat_p4<40><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n);
+    run_pat("P4  1 lane sector 0 + 80% second sector", [&] { pat_p4<80><<<blocks, threads>>>(buf, bytes / 128, iters, out); }, n);
+}
+
 int main (int argc, char** argv)
 {
     if (argc > 1) {
@@ -143,6 +244,8 @@ int main (int argc, char** argv)
         run_v8<32>(buf, bytes, out); run_v8<64>(buf, bytes, out); run_v8<128>(buf, bytes, out);
         run_coop<32>(buf, bytes, out); run_coop<64>(buf, bytes, out); run_coop<128>(buf, bytes, out); run_coop<256>(buf, bytes, out);
     }
+    printf("--- layout access patterns, working set 16 GB\n");
+    run_patterns(buf, 16ull << 30, out);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
