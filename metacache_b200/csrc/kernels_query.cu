@@ -227,23 +227,10 @@ constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk s
 template <class K>
 __host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
     // sdata[32] u64 | stage[kStage] K | hkeys[T] K | hcnt[T] u32 | hits[T/2+32] u32 | sbase[36] u32 |
-    // misc[36] u32 | list[T/2+32] u16
+    // ssec[36] u32 | chosen[32] u32 | list[T/2+32] u16
     const size_t b = 32 * 8 + size_t(kStage) * sizeof(K) + size_t(T) * sizeof(K) + size_t(T) * 4
-                   + (size_t(T) / 2 + 32) * 6 + 36 * 4 + 36 * 4;
+                   + (size_t(T) / 2 + 32) * 6 + 36 * 4 + 36 * 4 + 32 * 4;
     return (b + 15) & ~size_t(15);
-}
-
-template <class K>
-__device__ __forceinline__ bool agg_insert_bounded (K* hkeys, uint32_t* hcnt, uint32_t mask, K v)
-{
-    uint32_t h = AggKey<K>::hash(v) & mask;
-    #pragma unroll 1
-    for (uint32_t probes = 0; probes < kMaxProbe; ++probes) {
-        const K old = AggKey<K>::cas(hkeys + h, v);
-        if (old == AggKey<K>::kEmpty || old == v) { atomicAdd(hcnt + h, 1u); return true; }
-        h = (h + 1) & mask;
-    }
-    return false;
 }
 
 template <class K>
@@ -258,11 +245,44 @@ __device__ __forceinline__ uint32_t agg_lookup (const K* hkeys, const uint32_t* 
     }
 }
 
+// 32 bytes of a bucket's location list (one sector: 8 packed / 4 wide locations)
+__device__ __forceinline__ void load_sector (const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// One wave of <= 32 locations (one per lane, `active` lanes) into the per-warp table; slots that
+// were empty are appended to `list` (D of them so far).  Returns false if the table is too full.
+template <class K>
+__device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* list, uint32_t mask, uint32_t dmax,
+                                          bool active, K v, uint32_t& D)
+{
+    bool isnew = false, failed = false;
+    uint32_t h = 0;
+    if (active) {
+        h = AggKey<K>::hash(v) & mask;
+        failed = true;
+        #pragma unroll 1
+        for (uint32_t probes = 0; probes < kMaxProbe; ++probes) {
+            const K old = AggKey<K>::cas(hkeys + h, v);
+            isnew = (old == AggKey<K>::kEmpty);
+            if (isnew || old == v) { atomicAdd(hcnt + h, 1u); failed = false; break; }
+            h = (h + 1) & mask;
+        }
+    }
+    const uint32_t nm = __ballot_sync(kFull, isnew);
+    if (isnew) list[D + __popc(nm & ((1u << lane_id()) - 1u))] = uint16_t(h);
+    D += __popc(nm);
+    return !(__any_sync(kFull, failed) || D > dmax);
+}
+
 template <class K>
 __global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T)
 {
     using AK = AggKey<K>;
+    constexpr uint32_t EPS = 32 / sizeof(K);                                   // locations per 32-byte sector
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T);
@@ -271,11 +291,23 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     K*        hkeys = stage + kStage;                                          // [T]   (16-byte aligned)
     uint32_t* hcnt  = reinterpret_cast<uint32_t*>(hkeys + T);                  // [T]
     uint32_t* hits  = hcnt + T;                                                // [T/2+32]
-    uint32_t* sbase = hits + (T / 2 + 32);                                     // [36]
-    uint32_t* misc  = sbase + 36;                                              // [0] overflow flag, [1..] chosen
-    uint16_t* list  = reinterpret_cast<uint16_t*>(misc + 36);                  // [T/2+32]
+    uint32_t* sbase = hits + (T / 2 + 32);                                     // [36] first staged location per lane
+    uint32_t* ssec  = sbase + 36;                                              // [36] first list sector per lane
+    uint32_t* chosen = ssec + 36;                                              // [32]
+    uint16_t* list  = reinterpret_cast<uint16_t*>(chosen + 32);                // [T/2+32] occupied table slots
     const uint32_t mask = T - 1, dmax = T / 2;
     const uint32_t wb = a.table.win_bits;
+    const uint32_t icap = inline_capacity(wb);
+
+    // the table is cleared once; every read removes exactly the slots it filled (list)
+    {
+        const uint4 e4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z4 = make_uint4(0, 0, 0, 0);
+        uint4* k4 = reinterpret_cast<uint4*>(hkeys);
+        uint4* c4 = reinterpret_cast<uint4*>(hcnt);
+        for (uint32_t i = lane; i < T * sizeof(K) / 16; i += 32) k4[i] = e4;
+        for (uint32_t i = lane; i < T / 4; i += 32) c4[i] = z4;
+    }
+    __syncwarp();
 
     // persistent warps: a warp keeps its shared-memory table and walks the reads with a grid
     // stride, so warp slots never idle behind the slowest read of a CTA
@@ -286,26 +318,17 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
     const uint32_t W = __ldg(a.max_win + q);
     mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
-    uint32_t sectors = 0, nfeat = 0, H = 0;
+    uint32_t sectors = 0, nfeat = 0, H = 0, D = 0;
 
     if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
         warp_stats(a, false, 0, 0, 0);
         continue;
     }
-    {   // clear the table with 128-bit stores (hkeys and hcnt are contiguous and 16-byte aligned)
-        const uint4 e4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z4 = make_uint4(0, 0, 0, 0);
-        uint4* k4 = reinterpret_cast<uint4*>(hkeys);
-        uint4* c4 = reinterpret_cast<uint4*>(hcnt);
-        for (uint32_t i = lane; i < T * sizeof(K) / 16; i += 32) k4[i] = e4;
-        for (uint32_t i = lane; i < T / 4; i += 32) c4[i] = z4;
-    }
-    if (lane == 0) misc[0] = 0;
-    __syncwarp();
 
     // ---- probe + aggregate -------------------------------------------------
     bool ok = true;
-    for (uint32_t c = 0; c < nslots; c += 32) {
+    for (uint32_t c = 0; c < nslots && ok; c += 32) {
         const uint32_t idx = c + lane;
         const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
         uint32_t size = 0; uint64_t data = 0;
@@ -314,139 +337,144 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         if (total == 0) continue;
         H += total;
+        const uint32_t sb = incl - size;
+        sbase[lane] = sb;
+        sdata[lane] = data;
+        if (lane == 31) sbase[32] = total;
         if (total <= kStage) {
-            // every lane copies ITS bucket (one 64-byte line per 16 packed / 8 wide locations, 128-bit
-            // loads) to its place in the staging buffer; then the warp inserts the dense list
-            const uint32_t sb = incl - size;
-            if (size) {
-                if (sizeof(K) == 4) {
-                    if (size <= 2) { stage[sb] = K(uint32_t(data)); if (size == 2) stage[sb + 1] = K(uint32_t(data >> 32)); }
-                    else {
-                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(a.table.values) + data);
-                        for (uint32_t i = 0; i < size; i += 4) {
-                            const uint4 x = __ldg(src + (i >> 2));
-                            stage[sb + i] = K(x.x);
-                            if (i + 1 < size) stage[sb + i + 1] = K(x.y);
-                            if (i + 2 < size) stage[sb + i + 2] = K(x.z);
-                            if (i + 3 < size) stage[sb + i + 3] = K(x.w);
-                        }
-                    }
-                } else {
-                    if (size == 1) stage[sb] = K(data);
-                    else {
-                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint64_t*>(a.table.values) + data);
-                        for (uint32_t i = 0; i < size; i += 2) {
-                            const uint4 x = __ldg(src + (i >> 1));
-                            stage[sb + i] = K((uint64_t(x.y) << 32) | x.x);
-                            if (i + 1 < size) stage[sb + i + 1] = K((uint64_t(x.w) << 32) | x.z);
+            // dense list of the chunk's locations.  Inline buckets come out of the slot; the others
+            // are fetched sector by sector (32 B), consecutive lanes taking consecutive sectors of a
+            // bucket, so that a bucket costs ONE memory request per 64-byte line
+            const bool islist = size > icap;
+            if (size != 0 && !islist) {
+                if (sizeof(K) == 4) { stage[sb] = K(uint32_t(data)); if (size == 2) stage[sb + 1] = K(uint32_t(data >> 32)); }
+                else stage[sb] = K(data);
+            }
+            const uint32_t nsec = islist ? (size + EPS - 1) / EPS : 0u;
+            const uint32_t sincl = warp_incl_scan(nsec);
+            const uint32_t U = __shfl_sync(kFull, sincl, 31);
+            ssec[lane] = sincl - nsec;
+            if (lane == 31) ssec[32] = U;
+            __syncwarp();
+            for (uint32_t u0 = 0; u0 < U; u0 += 32) {
+                const uint32_t u = u0 + lane;
+                if (u < U) {
+                    uint32_t b = 0;
+                    #pragma unroll
+                    for (uint32_t step = 16; step > 0; step >>= 1)
+                        if (ssec[b + step] <= u) b += step;
+                    const uint32_t j = (u - ssec[b]) * EPS;            // first location of my sector
+                    const uint32_t o = sbase[b], n = sbase[b + 1] - o;
+                    uint32_t r[8];
+                    load_sector(static_cast<const K*>(a.table.values) + sdata[b] + j, r);
+                    #pragma unroll
+                    for (uint32_t t = 0; t < EPS; ++t) {
+                        if (j + t < n) {
+                            if (sizeof(K) == 4) stage[o + j + t] = K(r[t]);
+                            else stage[o + j + t] = K((uint64_t(r[2 * t + 1]) << 32) | r[2 * t]);
                         }
                     }
                 }
             }
             __syncwarp();
-            for (uint32_t p = lane; p < total; p += 32)
-                if (!agg_insert_bounded<K>(hkeys, hcnt, mask, stage[p])) misc[0] = 1;
-        } else {
-        sbase[lane] = incl - size;
-        sdata[lane] = data;
-        if (lane == 31) sbase[32] = total;
-        __syncwarp();
-        // waves of 4 x 32 locations: issue all loads of a wave, then insert
-        for (uint32_t p0 = 0; p0 < total; p0 += 128) {
-            K v[4];
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t p = p0 + u * 32 + lane;
-                v[u] = AK::kEmpty;
-                if (p < total) {
-                    uint32_t b = 0;
-                    #pragma unroll
-                    for (uint32_t step = 16; step > 0; step >>= 1)
-                        if (sbase[b + step] <= p) b += step;
-                    const uint32_t sb = sbase[b];
-                    v[u] = AK::load(a.table, sdata[b], sbase[b + 1] - sb, p - sb);
-                }
+            for (uint32_t p0 = 0; p0 < total && ok; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, p < total, p < total ? stage[p] : AK::kEmpty, D);
             }
-            #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (v[u] != AK::kEmpty && !agg_insert_bounded<K>(hkeys, hcnt, mask, v[u])) misc[0] = 1;
-        }
+        } else {
+            __syncwarp();
+            // waves of 4 x 32 locations: issue all loads of a wave, then insert
+            for (uint32_t p0 = 0; p0 < total && ok; p0 += 128) {
+                K v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t p = p0 + u * 32 + lane;
+                    v[u] = AK::kEmpty;
+                    if (p < total) {
+                        uint32_t b = 0;
+                        #pragma unroll
+                        for (uint32_t step = 16; step > 0; step >>= 1)
+                            if (sbase[b + step] <= p) b += step;
+                        const uint32_t o = sbase[b];
+                        v[u] = AK::load(a.table, sdata[b], sbase[b + 1] - o, p - o);
+                    }
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok) ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, v[u] != AK::kEmpty, v[u], D);
+            }
         }
         __syncwarp();
-        if (*reinterpret_cast<volatile uint32_t*>(misc) != 0) { ok = false; break; }
     }
 
-    if (ok && H == 0) {
-        if (lane == 0) write_empty(top, 0, a.maxc);
-        warp_stats(a, true, 0, nfeat, sectors);
-        continue;
-    }
-    // ---- distinct locations: compact the occupied slots ----------------------
-    uint32_t D = 0;
-    if (ok) {
-        for (uint32_t base = 0; base < T && D <= dmax; base += 32) {
-            const bool o = hkeys[base + lane] != AK::kEmpty;
-            const uint32_t occ = __ballot_sync(kFull, o);
-            if (o) list[D + __popc(occ & ((1u << lane) - 1u))] = uint16_t(base + lane);
-            D += __popc(occ);
+    if (ok && H != 0) {
+        // ---- hits(j) per distinct location; lane-local best and best of another target ----
+        // order: (hits desc, location asc)
+        uint32_t c1 = 0, c2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
+        for (uint32_t j = lane; j < D; j += 32) {
+            const uint32_t slot = list[j];
+            const K k = hkeys[slot];
+            uint32_t c = hcnt[slot];
+            const uint32_t win = AK::win(k, wb);
+            for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup<K>(hkeys, hcnt, mask, K(k - d));
+            hits[j] = c;
+            if (c > c1 || (c == c1 && k < k1)) {
+                if (c1 != 0 && AK::tgt(k1, wb) != AK::tgt(k, wb)) { c2 = c1; k2 = k1; }
+                c1 = c; k1 = k;
+            } else if (AK::tgt(k, wb) != AK::tgt(k1, wb) && (c > c2 || (c == c2 && k < k2))) { c2 = c; k2 = k; }
         }
-        if (D > dmax) ok = false;
-    }
-    if (!ok) {
+        __syncwarp();
+        // ---- top-k distinct targets ----------------------------------------------
+        uint32_t c = 0, last = 0xFFFFFFFFu;
+        for (; c < a.maxc; ++c) {
+            uint32_t best_c = c1; K best_k = k1;
+            if (c == 1) {
+                // second round: a lane's best outside the winning target is its best, or its runner-up
+                if (c1 != 0 && AK::tgt(k1, wb) == last) { best_c = c2; best_k = k2; }
+            } else if (c > 1) {
+                best_c = 0; best_k = AK::kEmpty;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const K k = hkeys[list[j]];
+                    const uint32_t tgt = AK::tgt(k, wb);
+                    bool taken = false;
+                    for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
+                    const uint32_t cj = hits[j];
+                    if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
+                }
+            }
+            const uint32_t wmax = __reduce_max_sync(kFull, best_c);
+            if (wmax == 0) break;
+            const bool cand = (best_c == wmax);
+            // smallest key among the lanes holding the maximum: (tgt, win) lexicographic
+            const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
+            const uint32_t wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
+            const uint32_t ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
+            if (lane == 0) {
+                // first window of the winning range: smallest present window in (ww-W, ww]
+                K ke;
+                if (sizeof(K) == 4) ke = K((wt << wb) | ww); else ke = K((uint64_t(wt) << 32) | ww);
+                uint32_t beg = ww;
+                for (uint32_t d = 1; d < W && d <= ww; ++d)
+                    if (agg_lookup<K>(hkeys, hcnt, mask, K(ke - d))) beg = ww - d;
+                top[c] = mcb200_candidate{wt, wmax, beg, ww};
+                chosen[c] = wt;
+            }
+            last = wt;
+            __syncwarp();
+        }
+        if (lane == 0) write_empty(top, c, a.maxc);
+    } else if (ok) {
+        if (lane == 0) write_empty(top, 0, a.maxc);
+    } else {
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
-        warp_stats(a, false, 0, nfeat, sectors);
-        continue;
     }
+    // ---- leave the table empty for the next read ----
     __syncwarp();
-    // ---- hits(j) per distinct location; lane-local best (hits desc, key asc) ----
-    uint32_t best_c = 0; K best_k = AK::kEmpty;
     for (uint32_t j = lane; j < D; j += 32) {
         const uint32_t slot = list[j];
-        const K k = hkeys[slot];
-        uint32_t c = hcnt[slot];
-        const uint32_t win = AK::win(k, wb);
-        for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup<K>(hkeys, hcnt, mask, k - d);
-        hits[j] = c;
-        if (c > best_c || (c == best_c && k < best_k)) { best_c = c; best_k = k; }
+        hkeys[slot] = AK::kEmpty; hcnt[slot] = 0;
     }
-    __syncwarp();
-    // ---- top-k distinct targets ----------------------------------------------
-    uint32_t* chosen = misc + 1;
-    uint32_t c = 0, last = 0xFFFFFFFFu;
-    for (; c < a.maxc; ++c) {
-        if (c > 0) {
-            best_c = 0; best_k = AK::kEmpty;
-            for (uint32_t j = lane; j < D; j += 32) {
-                const K k = hkeys[list[j]];
-                const uint32_t tgt = AK::tgt(k, wb);
-                bool taken = (tgt == last);
-                for (uint32_t i = 0; i + 1 < c; ++i) taken |= (chosen[i] == tgt);
-                const uint32_t cj = hits[j];
-                if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
-            }
-        }
-        const uint32_t wmax = __reduce_max_sync(kFull, best_c);
-        if (wmax == 0) break;
-        const bool cand = (best_c == wmax);
-        // smallest key among the lanes holding the maximum: (tgt, win) lexicographic
-        const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
-        const uint32_t wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
-        const uint32_t ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
-        if (lane == 0) {
-            // first window of the winning range: smallest present window in (ww-W, ww]
-            K ke;
-            if (sizeof(K) == 4) ke = K((wt << wb) | ww); else ke = K((uint64_t(wt) << 32) | ww);
-            uint32_t beg = ww;
-            for (uint32_t d = 1; d < W && d <= ww; ++d)
-                if (agg_lookup<K>(hkeys, hcnt, mask, ke - d)) beg = ww - d;
-            top[c] = mcb200_candidate{wt, wmax, beg, ww};
-            chosen[c] = wt;
-        }
-        last = wt;
-        __syncwarp();
-    }
-    if (lane == 0) write_empty(top, c, a.maxc);
-    warp_stats(a, true, H, nfeat, sectors);
+    warp_stats(a, ok, ok ? H : 0, nfeat, sectors);
     __syncwarp();
     }
 }
