@@ -156,6 +156,111 @@ __device__ __forceinline__ WinDesc window_desc (uint32_t w, const uint32_t* __re
     return d;
 }
 
+// ---------------------------------------------------------------------------
+// one window per WARP (any geometry): lanes hash 4 k-mers each, the s smallest
+// unique values are selected with warp-min reductions.  `sc`/`sa` = staged codes /
+// ambiguity bits whose first base is `base`; dst = the window's row of `feats`.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_sketch_window (const WinDesc d, const uint32_t* sc, const uint32_t* sa,
+                                                    uint32_t base, const SketchParams& p, uint32_t* dst,
+                                                    uint32_t lane)
+{
+    const uint32_t kshift = 32u - 2u * p.k;
+    const uint32_t nk = (d.n >= p.k) ? (d.n - p.k + 1) : 0u;
+    const uint32_t s_eff = min(p.s, nk);
+    if (nk <= 32) {
+        // short window (trailing windows, short reads): one k-mer per lane, one 32-wide
+        // register sort, keep the first s_eff distinct values
+        uint32_t v = kNoFeature;
+        if (lane < nk) {
+            const uint32_t rel = d.start + lane - base;
+            const uint32_t wi = rel >> 4, o = rel & 15u;
+            const uint32_t x = __funnelshift_l(sc[wi + 1], sc[wi], 2 * o);
+            const uint32_t ai = rel >> 5, ao = rel & 31u;
+            const uint32_t A = __funnelshift_l(sa[ai + 1], sa[ai], ao);
+            if ((A >> (32u - p.k)) == 0) v = hash32(canonical32(x >> kshift, p.k));
+        }
+        #pragma unroll
+        for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
+            #pragma unroll
+            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                const uint32_t other = __shfl_xor_sync(kFull, v, j);
+                const bool take_min = (((lane & k2) == 0) == ((lane & j) == 0));
+                v = take_min ? min(v, other) : max(v, other);
+            }
+        }
+        const uint32_t prev = __shfl_up_sync(kFull, v, 1);
+        const bool keep = (v != kNoFeature) && (lane == 0 || v != prev);
+        const uint32_t km = __ballot_sync(kFull, keep);
+        const uint32_t pos = __popc(km & ((1u << lane) - 1u));
+        const uint32_t nkeep = min(uint32_t(__popc(km)), s_eff);
+        if (keep && pos < s_eff) dst[pos] = v;
+        if (lane < p.s && lane >= nkeep) dst[lane] = kNoFeature;
+        return;
+    }
+    uint32_t run = kNoFeature;
+    for (uint32_t q0 = 0; q0 < nk; q0 += 128) {
+        const uint32_t q   = q0 + 4 * lane;          // first k-mer of this lane
+        const uint32_t rel = d.start + q - base;
+        uint32_t v[4] = {kNoFeature, kNoFeature, kNoFeature, kNoFeature};
+        if (q < nk) {
+            const uint32_t wi = rel >> 4, o = rel & 15u;
+            const uint32_t W0 = sc[wi], W1 = sc[wi + 1], W2 = sc[wi + 2];
+            const uint32_t ai = rel >> 5, ao = rel & 31u;
+            const uint32_t A  = __funnelshift_l(sa[ai + 1], sa[ai], ao);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t oj = o + j;
+                const uint32_t x = (oj < 16u) ? __funnelshift_l(W1, W0, 2 * oj)
+                                              : __funnelshift_l(W2, W1, 2 * (oj - 16u));
+                const uint32_t kmer = x >> kshift;
+                const uint32_t ambig = (A << j) >> (32u - p.k);
+                if (q + j < nk && ambig == 0) v[j] = hash32(canonical32(kmer, p.k));
+            }
+        }
+        uint32_t newrun = kNoFeature;
+        if (nk <= 128) {
+            // single chunk (the default geometry): keep the lane's 4 hashes sorted so the
+            // lane minimum is v[0] and "remove the selected value" is a shift
+            #define MCB_CE(a, b) { const uint32_t lo_ = min(v[a], v[b]); v[b] = max(v[a], v[b]); v[a] = lo_; }
+            MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
+            // duplicates inside the lane (tandem repeats): keep one, re-sort
+            if (__any_sync(kFull, (v[0] == v[1] && v[1] != kNoFeature) || (v[1] == v[2] && v[2] != kNoFeature) || (v[2] == v[3] && v[3] != kNoFeature))) {
+                const bool d1 = v[1] == v[0], d2 = v[2] == v[1], d3 = v[3] == v[2];
+                if (d1) v[1] = kNoFeature;
+                if (d2) v[2] = kNoFeature;
+                if (d3) v[3] = kNoFeature;
+                MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
+            }
+            #undef MCB_CE
+            #pragma unroll 4
+            for (uint32_t r = 0; r < s_eff; ++r) {
+                const uint32_t wm = __reduce_min_sync(kFull, v[0]);
+                if (wm == kNoFeature) break;
+                newrun = (lane == r) ? wm : newrun;
+                const bool hit = (v[0] == wm);
+                v[0] = hit ? v[1] : v[0];
+                v[1] = hit ? v[2] : v[1];
+                v[2] = hit ? v[3] : v[2];
+                v[3] = hit ? kNoFeature : v[3];
+            }
+        } else {
+            // s smallest unique values of {v[0..3] of all lanes} U {run of all lanes}
+            for (uint32_t r = 0; r < s_eff; ++r) {
+                const uint32_t m = min(min(min(v[0], v[1]), min(v[2], v[3])), run);
+                const uint32_t wm = __reduce_min_sync(kFull, m);
+                if (wm == kNoFeature) break;
+                if (lane == r) newrun = wm;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = (v[j] == wm) ? kNoFeature : v[j];
+                run = (run == wm) ? kNoFeature : run;
+            }
+        }
+        run = newrun;
+    }
+    if (lane < p.s) dst[lane] = run;
+}
+
 __global__ void __launch_bounds__(kSketchThreads)
 sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ amb,
                const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_win_off,
@@ -210,7 +315,6 @@ sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ 
         __syncthreads();
         if (tid == 0) issue_copy(tile, 0);
     }
-    const uint32_t kshift = 32u - 2u * p.k;
     for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t cur = it & 1u, nxt = cur ^ 1u;
         const uint32_t next_tile = tile + gridDim.x;
@@ -225,104 +329,200 @@ sketch_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ 
         const uint32_t w0 = tile * tile_windows;
         const uint32_t cnt = min(tile_windows, nwin - w0);
 
-        for (uint32_t i = warp; i < cnt; i += kSketchWarps) {
-            const WinDesc d = s_desc[cur * tile_windows + i];
-            const uint32_t nk = (d.n >= p.k) ? (d.n - p.k + 1) : 0u;
+        for (uint32_t i = warp; i < cnt; i += kSketchWarps)
+            warp_sketch_window(s_desc[cur * tile_windows + i], sc, sa, base, p, feats + uint64_t(w0 + i) * p.s, lane);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sketch, fast path (windows of <= 256 bases, sketches of <= 16 features): one
+// window per THREAD.
+//   1. the thread walks its window base by base: rolling forward / reverse
+//      complement k-mers (two shifts instead of a bit reversal per k-mer),
+//      ambiguity as a smeared bit mask per 16 bases, hash; hashes below a threshold
+//      chosen so that ~24 of the window's k-mers pass (all of them for windows of
+//      <= 32 k-mers) go to the thread's candidate column in shared memory
+//   2. the thread inserts its candidates into a sorted 16-entry register array
+//      (a compare-exchange chain), i.e. keeps the 16 smallest
+// That is the reference's "s smallest unique hashes" as long as the array ends up
+// with s distinct values; windows with > 32 candidates, too few candidates below
+// the threshold or equal values left in the array (~5 %) are redone by a warp with
+// warp_sketch_window, which makes no assumption.  A thread takes two consecutive
+// windows, so the long and the short window of a 150 bp read load every lane alike.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kFastThreads = 128;
+constexpr uint32_t kFastTile    = 2 * kFastThreads;   // windows per tile
+constexpr uint32_t kFastMaxWin  = 256;                 // longest window the fast path stages
+constexpr uint32_t kFastMaxS    = 16;                  // register array
+constexpr uint32_t kCandStride  = kFastThreads + 1;
+constexpr float    kCandTarget  = 24.0f;               // expected candidates per window
+
+__device__ __forceinline__ uint32_t smear_right (uint32_t x, uint32_t k) {
+    // bit i of the result = OR of bits i .. i+k-1 of x (towards the MSB), k >= 1
+    uint32_t r = x, s = 1;
+    while (2 * s <= k) { r |= r >> s; s *= 2; }
+    return r | (r >> (k - s));
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+sketch_fast_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ amb,
+                    const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_win_off,
+                    const uint32_t* __restrict__ win_seq, const uint32_t* __restrict__ d_nwin,
+                    SketchParams p, uint32_t* __restrict__ feats, uint32_t stage_bases)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // [stage0 codes][stage1 codes][stage0 amb][stage1 amb][desc0][desc1][cand 32 x 129][redo 256][n_redo, base0, base1][bars]
+    uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_amb   = s_codes + 2 * (stage_bases / 16);
+    WinDesc*  s_desc  = reinterpret_cast<WinDesc*>(s_amb + 2 * (stage_bases / 32));
+    uint32_t* s_cand  = reinterpret_cast<uint32_t*>(s_desc + 2 * kFastTile);
+    uint32_t* s_redo  = s_cand + 32 * kCandStride;
+    uint32_t* s_misc  = s_redo + kFastTile;             // [0] windows to redo, [1..2] first base of a stage
+    uint32_t* s_base  = s_misc + 1;
+    uint64_t* s_bar   = reinterpret_cast<uint64_t*>(s_misc + 4);
+
+    const uint32_t nwin   = *d_nwin;
+    const uint32_t ntiles = (nwin + kFastTile - 1) / kFastTile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_misc[0] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    auto make_desc = [&] (uint32_t tile, uint32_t stage) {
+        for (uint32_t i = tid; i < kFastTile; i += kFastThreads) {
+            const uint32_t w = tile * kFastTile + i;
+            WinDesc d{0, 0};
+            if (w < nwin) d = window_desc(w, seq_off, seq_win_off, win_seq, p);
+            s_desc[stage * kFastTile + i] = d;
+        }
+    };
+    auto issue_copy = [&] (uint32_t tile, uint32_t stage) {   // thread 0 only
+        const uint32_t w0 = tile * kFastTile;
+        const uint32_t cnt = min(kFastTile, nwin - w0);
+        const WinDesc f = s_desc[stage * kFastTile];
+        const WinDesc l = s_desc[stage * kFastTile + cnt - 1];
+        const uint32_t lo = f.start & ~(kAlignBases - 1);
+        uint32_t hi = (l.start + l.n + kSlackBases + kAlignBases - 1) & ~(kAlignBases - 1);
+        if (hi - lo > stage_bases) hi = lo + stage_bases;      // never exceeds by construction
+        const uint32_t cb = (hi - lo) / 4, ab = (hi - lo) / 8;
+        s_base[stage] = lo;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[stage], cb + ab);
+        bulk_g2s(s_codes + stage * (stage_bases / 16), codes + lo / 16, cb, &s_bar[stage]);
+        bulk_g2s(s_amb + stage * (stage_bases / 32), amb + lo / 32, ab, &s_bar[stage]);
+    };
+
+    const uint32_t k = p.k;
+    const uint32_t kmask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t rcsh = 2 * k - 2;
+    uint32_t* mycand = s_cand + tid;
+
+    uint32_t tile = blockIdx.x;
+    if (tile < ntiles) {
+        make_desc(tile, 0);
+        __syncthreads();
+        if (tid == 0) issue_copy(tile, 0);
+    }
+    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t cur = it & 1u, nxt = cur ^ 1u;
+        const uint32_t next_tile = tile + gridDim.x;
+        if (next_tile < ntiles) make_desc(next_tile, nxt);
+        __syncthreads();
+        if (tid == 0 && next_tile < ntiles) issue_copy(next_tile, nxt);
+        mbar_wait(&s_bar[cur], (it >> 1) & 1u);
+
+        const uint32_t* sc = s_codes + cur * (stage_bases / 16);
+        const uint32_t* sa = s_amb + cur * (stage_bases / 32);
+        const uint32_t base = s_base[cur];
+        const uint32_t w0 = tile * kFastTile;
+        const uint32_t cnt = min(kFastTile, nwin - w0);
+
+        #pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+            const uint32_t i = 2 * tid + half;
+            if (i >= cnt) break;
+            const WinDesc d = s_desc[cur * kFastTile + i];
+            const uint32_t nk = (d.n >= k) ? (d.n - k + 1) : 0u;
             const uint32_t s_eff = min(p.s, nk);
-            if (nk <= 32) {
-                // short window (trailing windows, short reads): one k-mer per lane, one 32-wide
-                // register sort, keep the first s_eff distinct values
-                uint32_t v = kNoFeature;
-                if (lane < nk) {
-                    const uint32_t rel = d.start + lane - base;
-                    const uint32_t wi = rel >> 4, o = rel & 15u;
-                    const uint32_t x = __funnelshift_l(sc[wi + 1], sc[wi], 2 * o);
-                    const uint32_t ai = rel >> 5, ao = rel & 31u;
-                    const uint32_t A = __funnelshift_l(sa[ai + 1], sa[ai], ao);
-                    if ((A >> (32u - p.k)) == 0) v = hash32(canonical32(x >> kshift, p.k));
-                }
+            // ---- 1. roll + hash + threshold ----
+            // all k-mers are candidates when they fit the column; else expect kCandTarget of them
+            const uint32_t thr = (nk <= 32) ? 0xFFFFFFFFu
+                                            : uint32_t(fminf(4294967040.0f, __fdividef(kCandTarget * 4294967296.0f, float(nk))));
+            uint32_t nc = 0, fwd = 0, rc = 0;
+            const uint32_t rel = d.start - base;
+            const uint32_t wi0 = rel >> 4, o2 = 2 * (rel & 15u);
+            uint32_t prev_amb = 0xFFFFu;                 // the 16 bases before the window count as ambiguous
+            #pragma unroll 1
+            for (uint32_t g = 0; 16 * g < d.n; ++g) {
+                const uint32_t Wg = __funnelshift_l(sc[wi0 + g + 1], sc[wi0 + g], o2);
+                const uint32_t apos = rel + 16 * g;
+                const uint32_t A16 = __funnelshift_l(sa[(apos >> 5) + 1], sa[apos >> 5], apos & 31u) >> 16;
+                // bit (15 - t) of `bad`: the k-mer ending at base 16 g + t has an ambiguous base or starts before the window
+                const uint32_t bad = smear_right((prev_amb << 16) | A16, k);
+                prev_amb = A16;
+                const uint32_t m = min(16u, d.n - 16 * g);
                 #pragma unroll
-                for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
-                    #pragma unroll
-                    for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
-                        const uint32_t other = __shfl_xor_sync(kFull, v, j);
-                        const bool take_min = (((lane & k2) == 0) == ((lane & j) == 0));
-                        v = take_min ? min(v, other) : max(v, other);
+                for (uint32_t t = 0; t < 16; ++t) {
+                    if (t < m) {
+                        const uint32_t c = (Wg >> (30 - 2 * t)) & 3u;
+                        fwd = ((fwd << 2) | c) & kmask;
+                        rc = (rc >> 2) | ((c ^ 3u) << rcsh);
+                        const uint32_t h = hash32(min(fwd, rc));
+                        if (!((bad >> (15 - t)) & 1u) && h < thr) {
+                            if (nc < 32) mycand[nc * kCandStride] = h;
+                            ++nc;
+                        }
                     }
                 }
-                const uint32_t prev = __shfl_up_sync(kFull, v, 1);
-                const bool keep = (v != kNoFeature) && (lane == 0 || v != prev);
-                const uint32_t km = __ballot_sync(kFull, keep);
-                const uint32_t pos = __popc(km & ((1u << lane) - 1u));
-                const uint32_t nkeep = min(uint32_t(__popc(km)), s_eff);
-                uint32_t* dst = feats + uint64_t(w0 + i) * p.s;
-                if (keep && pos < s_eff) dst[pos] = v;
-                if (lane < p.s && lane >= nkeep) dst[lane] = kNoFeature;
-                continue;
             }
-            uint32_t run = kNoFeature;
-            for (uint32_t q0 = 0; q0 < nk; q0 += 128) {
-                const uint32_t q   = q0 + 4 * lane;          // first k-mer of this lane
-                const uint32_t rel = d.start + q - base;
-                uint32_t v[4] = {kNoFeature, kNoFeature, kNoFeature, kNoFeature};
-                if (q < nk) {
-                    const uint32_t wi = rel >> 4, o = rel & 15u;
-                    const uint32_t W0 = sc[wi], W1 = sc[wi + 1], W2 = sc[wi + 2];
-                    const uint32_t ai = rel >> 5, ao = rel & 31u;
-                    const uint32_t A  = __funnelshift_l(sa[ai + 1], sa[ai], ao);
+            // ---- 2. the 16 smallest candidates, ascending ----
+            bool redo = nc > 32;
+            if (!redo) {
+                uint32_t a[kFastMaxS];
+                #pragma unroll
+                for (uint32_t j = 0; j < kFastMaxS; ++j) a[j] = kNoFeature;
+                #pragma unroll 1
+                for (uint32_t c = 0; c < nc; ++c) {
+                    uint32_t x = mycand[c * kCandStride];
                     #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t oj = o + j;
-                        const uint32_t x = (oj < 16u) ? __funnelshift_l(W1, W0, 2 * oj)
-                                                      : __funnelshift_l(W2, W1, 2 * (oj - 16u));
-                        const uint32_t kmer = x >> kshift;
-                        const uint32_t ambig = (A << j) >> (32u - p.k);
-                        if (q + j < nk && ambig == 0) v[j] = hash32(canonical32(kmer, p.k));
+                    for (uint32_t j = 0; j < kFastMaxS; ++j) {
+                        const uint32_t lo = min(a[j], x);
+                        x = max(a[j], x);
+                        a[j] = lo;
                     }
                 }
-                uint32_t newrun = kNoFeature;
-                if (nk <= 128) {
-                    // single chunk (the default geometry): keep the lane's 4 hashes sorted so the
-                    // lane minimum is v[0] and "remove the selected value" is a shift
-                    #define MCB_CE(a, b) { const uint32_t lo_ = min(v[a], v[b]); v[b] = max(v[a], v[b]); v[a] = lo_; }
-                    MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
-                    // duplicates inside the lane (tandem repeats): keep one, re-sort
-                    if (__any_sync(kFull, (v[0] == v[1] && v[1] != kNoFeature) || (v[1] == v[2] && v[2] != kNoFeature) || (v[2] == v[3] && v[3] != kNoFeature))) {
-                        const bool d1 = v[1] == v[0], d2 = v[2] == v[1], d3 = v[3] == v[2];
-                        if (d1) v[1] = kNoFeature;
-                        if (d2) v[2] = kNoFeature;
-                        if (d3) v[3] = kNoFeature;
-                        MCB_CE(0, 1) MCB_CE(2, 3) MCB_CE(0, 2) MCB_CE(1, 3) MCB_CE(1, 2)
-                    }
-                    #undef MCB_CE
-                    #pragma unroll 4
-                    for (uint32_t r = 0; r < s_eff; ++r) {
-                        const uint32_t wm = __reduce_min_sync(kFull, v[0]);
-                        if (wm == kNoFeature) break;
-                        newrun = (lane == r) ? wm : newrun;
-                        const bool hit = (v[0] == wm);
-                        v[0] = hit ? v[1] : v[0];
-                        v[1] = hit ? v[2] : v[1];
-                        v[2] = hit ? v[3] : v[2];
-                        v[3] = hit ? kNoFeature : v[3];
-                    }
-                } else {
-                    // s smallest unique values of {v[0..3] of all lanes} U {run of all lanes}
-                    for (uint32_t r = 0; r < s_eff; ++r) {
-                        const uint32_t m = min(min(min(v[0], v[1]), min(v[2], v[3])), run);
-                        const uint32_t wm = __reduce_min_sync(kFull, m);
-                        if (wm == kNoFeature) break;
-                        if (lane == r) newrun = wm;
+                uint32_t have = 0; bool dup = false;
+                #pragma unroll
+                for (uint32_t j = 0; j < kFastMaxS; ++j) {
+                    have += (a[j] != kNoFeature);
+                    if (j + 1 < kFastMaxS) dup |= (a[j] == a[j + 1]) && (a[j] != kNoFeature);
+                }
+                redo = dup || (have < s_eff && nk > 32);
+                if (!redo) {
+                    uint32_t* dst = feats + uint64_t(w0 + i) * p.s;
+                    if (p.s == kFastMaxS) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst);
+                        d4[0] = make_uint4(a[0], a[1], a[2], a[3]);   d4[1] = make_uint4(a[4], a[5], a[6], a[7]);
+                        d4[2] = make_uint4(a[8], a[9], a[10], a[11]); d4[3] = make_uint4(a[12], a[13], a[14], a[15]);
+                    } else {
                         #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = (v[j] == wm) ? kNoFeature : v[j];
-                        run = (run == wm) ? kNoFeature : run;
+                        for (uint32_t j = 0; j < kFastMaxS; ++j) if (j < p.s) dst[j] = a[j];
                     }
                 }
-                run = newrun;
             }
-            if (lane < p.s) feats[uint64_t(w0 + i) * p.s + lane] = run;
+            if (redo) s_redo[atomicAdd(&s_misc[0], 1u)] = i;
         }
         __syncthreads();
+        // ---- the few windows the fast path could not settle: one warp each ----
+        const uint32_t nredo = s_misc[0];
+        for (uint32_t r = warp; r < nredo; r += kFastThreads / 32) {
+            const uint32_t i = s_redo[r];
+            warp_sketch_window(s_desc[cur * kFastTile + i], sc, sa, base, p, feats + uint64_t(w0 + i) * p.s, lane);
+        }
+        __syncthreads();
+        if (tid == 0) s_misc[0] = 0;
     }
 }
 
@@ -330,6 +530,28 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
                     const uint32_t* seq_win_off, const uint32_t* win_seq, const uint32_t* d_nwin,
                     SketchParams p, uint32_t* feats, int sm_count, cudaStream_t st)
 {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(sketch_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    static const int ctas_per_sm = [] { const char* e = getenv("MCB200_SKETCH_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
+    static const bool no_fast = getenv("MCB200_SKETCH_WARP") != nullptr;     // testing aid: warp-per-window kernel only
+    if (p.w <= kFastMaxWin && p.s <= kFastMaxS && !no_fast) {
+        uint32_t stage_bases = kFastTile * p.w + kAlignBases + kSlackBases + kAlignBases;
+        stage_bases = (stage_bases + kAlignBases - 1) & ~(kAlignBases - 1);
+        const size_t smem = 2 * (stage_bases / 4) + 2 * (stage_bases / 8) + 2 * kFastTile * sizeof(WinDesc)
+                          + 32 * kCandStride * 4 + kFastTile * 4 + 4 * sizeof(uint32_t) + 2 * sizeof(uint64_t);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_fast_kernel, int(kFastThreads), smem);
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2 * ctas_per_sm) per_sm = 2 * ctas_per_sm;
+        sketch_fast_kernel<<<sm_count * per_sm, kFastThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
+                                                                          d_nwin, p, feats, stage_bases);
+        count_launch();
+        return;
+    }
     // tile: as many windows as fit a ~24 KB stage, at most 64
     uint32_t tile_windows = 64;
     while (tile_windows > kSketchWarps && uint64_t(tile_windows) * p.w > 96 * 1024) tile_windows /= 2;
@@ -338,12 +560,6 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
     const size_t smem = 2 * (stage_bases / 4) + 2 * (stage_bases / 8)
                       + 2 * tile_windows * sizeof(WinDesc) + 2 * sizeof(uint32_t) + 8
                       + 2 * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    static const int ctas_per_sm = [] { const char* e = getenv("MCB200_SKETCH_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
     const int grid = sm_count * ctas_per_sm;
     sketch_kernel<<<grid, kSketchThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
                                                       d_nwin, p, feats, tile_windows, stage_bases);

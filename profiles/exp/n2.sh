@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py > gpurun_out/multi_gpu_check_n$N.log 2>&1
+tail -3 gpurun_out/multi_gpu_check_n$N.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.log 2>&1
+tail -1 gpurun_out/bench_n$N.log | cut -c1-2500
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1
+tail -1 gpurun_out/bench_ref_n$N.log | cut -c1-600
