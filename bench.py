@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+                    help="C2: 150 bp reads (the metric's configuration, default); C3: long reads (200-19000 bp)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = 10 M for C2, 2 M for C3)")
     ap.add_argument("--targets", type=int, default=50_000, help="targets per database part")
     ap.add_argument("--target-len", type=int, default=100_000)
     ap.add_argument("--slot-reads", type=int, default=1_000_000, help="reads per host batch slot (e2e)")
@@ -137,14 +139,18 @@ def build_part(args, part, device):
 
 
 def make_reads(args, bases, rank, device):
+    """-> (flat uint8 bases on the device, int64 offsets [n+1] on the device)"""
     import torch
     from metacache_b200 import synth
+    if args.workload == "C3":
+        return synth.make_long_reads(args.reads, bases, args.targets, args.target_len,
+                                     seed=synth.SEED_RLONG + 1000 * rank, device=device)
     # every rank owns a different slice of the global read set (seed offset by rank); reads are
     # sampled from the rank's own part (the other parts see them as mostly-missing queries,
     # plus whatever the shared 16-mer space yields)
     reads = synth.make_reads_150(args.reads, bases, args.targets, args.target_len, READ_LEN,
                                  seed=synth.SEED_R150 + 1000 * rank, device=device)
-    return reads
+    return reads.reshape(-1), torch.arange(args.reads + 1, dtype=torch.int64, device=device) * READ_LEN
 
 
 def export_reference_db(args, db, wins, part):
@@ -164,35 +170,43 @@ def export_reference_db(args, db, wins, part):
     return base
 
 
-def write_reads_txt(path, reads_np):
-    n = reads_np.shape[0]
-    buf = np.empty((n, reads_np.shape[1] + 1), np.uint8)
-    buf[:, :-1] = reads_np
-    buf[:, -1] = ord("\n")
-    buf.tofile(path)
+def write_reads_txt(path, flat_np, offs_np):
+    """one read per line"""
+    n = len(offs_np) - 1
+    lens = np.diff(offs_np)
+    out = np.full(int(offs_np[-1] - offs_np[0]) + n, ord("\n"), np.uint8)
+    dst = (np.arange(len(flat_np), dtype=np.int64) + np.repeat(np.arange(n, dtype=np.int64), lens))
+    out[dst] = flat_np
+    out.tofile(path)
 
 
-def cpu_reference_run(base, reads_np, threads, passes):
+def cpu_reference_run(base, flat_np, offs_np, threads, passes):
     """the reference's own hot path (oracle/_ref/mc_ref_harness links the unmodified reference
     objects) on `threads` host threads; returns dict with per-pass seconds"""
     from oracle import refio
     if not os.path.exists(refio.HARNESS):
         return None
-    rt = base + f".reads{reads_np.shape[0]}.txt"
+    rt = base + f".reads{len(offs_np) - 1}_{int(offs_np[-1] - offs_np[0])}.txt"
     if not os.path.exists(rt):
-        write_reads_txt(rt, reads_np)
+        write_reads_txt(rt, flat_np, offs_np)
     return refio.run_harness(base, rt, "-", threads=threads, repeat=passes, sketches=0, allhits=0)
 
 
-def cpu_port_run(db, reads_np):
+def cpu_port_run(db, flat_np, offs_np):
     """fallback CPU baseline: the C restatement (oracle/mc_oracle.c), one thread"""
     from oracle import mc_oracle as O
     keys, sizes, values = db.export_part(0)
     tab = O.Table(keys, sizes, values)
     t0 = time.time()
-    for r in reads_np:
-        O.query(tab, r.tobytes(), b"")
+    for i in range(len(offs_np) - 1):
+        O.query(tab, flat_np[offs_np[i]:offs_np[i + 1]].tobytes(), b"")
     return time.time() - t0
+
+
+def host_sample(flat, offs, n):
+    """first n reads as host arrays (bases, offsets starting at 0)"""
+    o = offs[:n + 1].cpu().numpy()
+    return flat[int(o[0]):int(o[-1])].cpu().numpy(), o - o[0]
 
 
 # --------------------------------------------------------------------------------------
@@ -220,38 +234,53 @@ def main():
     part = rank if world > 1 else 0
     threads = os.cpu_count() or 1
 
+    if not args.reads:
+        args.reads = 10_000_000 if args.workload == "C2" else 2_000_000
+    if args.workload == "C3" and world > 1:
+        raise SystemExit("workload C3 is a single-GPU configuration (BASELINE.json configs[2])")
     db, bases, wins, dbinfo = build_part(args, part, device)
-    reads = make_reads(args, bases, rank, device)            # [n, 150] uint8 on device
+    flat, offs = make_reads(args, bases, rank, device)       # uint8 bases back to back + int64 offsets, on the device
     del bases
     torch.cuda.empty_cache()
     nq = args.reads
-    workload = (f"C2: {nq} x {READ_LEN}bp synthetic reads (R150) vs {args.targets}-target x "
-                f"{args.target_len}bp synthetic db (DB-S, k=16 s=16 w=127), "
-                + ("single partition" if world == 1 else f"{world}-way target-partitioned, one part per GPU"))
-    config = {"workload": workload, "reads_per_gpu": nq, "read_len": READ_LEN, "targets_per_part": args.targets,
+    n_bases = int(offs[-1].item())
+    part_desc = "single partition" if world == 1 else f"{world}-way target-partitioned, one part per GPU"
+    if args.workload == "C2":
+        metric = "reads_per_second_150bp"
+        workload = (f"C2: {nq} x {READ_LEN}bp synthetic reads (R150) vs {args.targets}-target x "
+                    f"{args.target_len}bp synthetic db (DB-S, k=16 s=16 w=127), " + part_desc)
+        read_len = READ_LEN
+    else:
+        metric = "reads_per_second_long"
+        workload = (f"C3: {nq} synthetic long reads (RLONG: 200-19000 bp, median 480, {n_bases / nq:.0f} bp mean) vs "
+                    f"{args.targets}-target x {args.target_len}bp synthetic db (DB-S, k=16 s=16 w=127), " + part_desc)
+        read_len = round(n_bases / nq, 1)
+    config = {"workload": workload, "reads_per_gpu": nq, "read_len": read_len, "targets_per_part": args.targets,
               "db": dbinfo, "l2": "inputs larger than L2 (reads %.1f GB + table %.1f GB per step)" %
-              (nq * READ_LEN / 1e9, dbinfo["table_gb"]), "parallelism": "db-sharded x%d" % world}
+              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": "db-sharded x%d" % world}
+    per_read_scale = READ_LEN * nq / n_bases                 # CPU samples are sized in 150 bp read equivalents
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
         if world > 1:
             config["reference_db"] = "part 0 only (1/%d of the sharded database)" % world
         base = export_reference_db(args, db, wins, 0)
-        sample = args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads)))
-        reads_np = reads[:sample].cpu().numpy()
+        sample = args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads) * per_read_scale))
+        flat_np, offs_np = host_sample(flat, offs, sample)
         passes = args.warmup + args.steps
-        r = cpu_reference_run(base, reads_np, threads, passes)
+        r = cpu_reference_run(base, flat_np, offs_np, threads, passes)
         if r is None:
-            t = cpu_port_run(db, reads_np[:20000])
-            val, kind, cores, ms = 20000 / t, "port", 1, t * 1e3
-            sample_desc = "first 20000 reads of the workload, oracle/mc_oracle.c"
+            n = int(20000 * per_read_scale)
+            t = cpu_port_run(db, flat_np, offs_np[:n + 1])
+            val, kind, cores, ms = n / t, "port", 1, t * 1e3
+            sample_desc = f"first {n} reads of the workload, oracle/mc_oracle.c"
         else:
             tt = r["passes"][-args.steps:]
             val, kind, cores, ms = sample * len(tt) / sum(tt), "reference", threads, 1e3 * sum(tt) / len(tt)
             sample_desc = (f"first {sample} reads of the workload per step, reference hot path "
                            f"(database::query_host) via oracle/_ref/mc_ref_harness, {threads} threads, "
                            f"db load {r['load_seconds']:.0f}s untimed")
-        print(json.dumps({"impl": "reference", "metric": "reads_per_second_150bp", "value": val, "unit": "reads/s",
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "reads/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64",
                           "data": "synthetic", "config": config,
@@ -262,11 +291,11 @@ def main():
 
     # ---------------- device-resident inputs ----------------
     sk = Sketching(**SK)
-    flat = reads.reshape(-1)
-    n_bases = nq * READ_LEN
-    seq_off = (torch.arange(nq + 1, dtype=torch.int64, device=device) * READ_LEN).to(torch.int32)
+    if n_bases >= (1 << 32) - 4096:
+        raise SystemExit("batch too large for 32-bit base offsets: lower --reads")
+    seq_off = offs.to(torch.int32)                            # (values < 2^32 wrap into the u32 the library reads)
     seq_qry = torch.arange(nq, dtype=torch.int32, device=device)
-    max_win = torch.full((nq,), 2 + READ_LEN // SK["winstride"], dtype=torch.int32, device=device)
+    max_win = (2 + (offs[1:] - offs[:-1]) // SK["winstride"]).to(torch.int32)
     stream = torch.cuda.Stream(device)
     sp = C.c_void_p(stream.cuda_stream)
     nq_total = nq * world
@@ -297,8 +326,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    if world == 1:
-        nw = L.mcb200_workspace_num_windows(ws)
+    nwin_launch = L.mcb200_workspace_num_windows(ws) if world == 1 else 2 * nq
     cnt = (C.c_uint64 * 8)()
     _lib.check(L.mcb200_workspace_counters(ws, cnt))         # resets the counters
     _lib.check(L.mcb200_workspace_set_profiling(ws, 1))
@@ -335,7 +363,6 @@ def main():
     calls = float(args.steps)
     n_launch = calls * world                                   # fused-kernel launches in the timed region
     feats_probed, locs, sectors = cnt[4] / n_launch, cnt[3] / n_launch, cnt[5] / n_launch
-    nwin_launch = 2 * nq
     alg_bytes = 4 * SK["sketchlen"] * nwin_launch + 16 * feats_probed + 8 * locs + 16 * MAXC * nq + 8 * nq
     k_ms = (stage[3] + stage[4]) / n_launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -368,22 +395,25 @@ def main():
     if world == 1:
         nslots = (nq + args.slot_reads - 1) // args.slot_reads
         per = args.slot_reads
-        host_reads = reads.cpu().numpy().reshape(-1)
+        host_reads = flat.cpu().numpy()
+        host_offs = offs.cpu().numpy().astype(np.uint64)
         del d_top
         L.mcb200_workspace_destroy(ws)
         ws = None
-        del flat, reads
+        del flat
         torch.cuda.empty_cache()
-        qb = _lib.check_ptr(L.mcb200_batch_create(db._h, per, per * READ_LEN + 64, MAXC, 0, nslots))
-        offs = (np.arange(per + 1, dtype=np.uint64) * READ_LEN)
+        slot_bases = max(int(host_offs[min(nq, (s + 1) * per)] - host_offs[s * per]) for s in range(nslots))
+        qb = _lib.check_ptr(L.mcb200_batch_create(db._h, per, slot_bases + 64, MAXC, 0, nslots))
         h2d = d2h = 0
         for s in range(nslots):
             n = min(per, nq - s * per)
-            chunk = host_reads[s * per * READ_LEN:(s * per + n) * READ_LEN]
-            added = _lib.check(L.mcb200_batch_add_reads(qb, s, chunk.ctypes.data, offs.ctypes.data, n, 0, 0,
+            so = host_offs[s * per:s * per + n + 1]
+            chunk = host_reads[int(so[0]):int(so[-1])]
+            so = np.ascontiguousarray(so - so[0])
+            added = _lib.check(L.mcb200_batch_add_reads(qb, s, chunk.ctypes.data, so.ctypes.data, n, 0, 0,
                                                         SK["winstride"]))
             assert added == n
-            h2d += n * READ_LEN + (n + 1) * 4 + n * 4 + n * 4
+            h2d += len(chunk) + (n + 1) * 4 + n * 4 + n * 4
             d2h += n * MAXC * 16
 
         def e2e_step():
@@ -409,7 +439,6 @@ def main():
                "wall_ms_per_step": round(sum(wall) / len(wall), 3), "slots": nslots,
                "api": "mcb200_batch_submit/wait over pinned host buffers (query_batch seam)"}
         # sanity: first reads' results identical on both paths is covered by tests; keep the sample
-        host_sample = host_reads
     else:
         # pinned host slice -> device, distributed pipeline, final tops of my slice -> pinned host
         pin_in = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
@@ -437,24 +466,24 @@ def main():
         e2e = {"value": nq_total / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(n_bases * world),
                "d2h_bytes_per_step": int(nq * MAXC * 16 * world), "ms_per_step": round(e2e_ms, 3),
                "api": "pinned host reads -> H2D -> sketch/all-gather/probe/all-to-all/merge -> D2H"}
-        host_sample = None
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
             base = export_reference_db(args, db, wins, 0)
-            sample = args.cpu_sample or int(min(nq, max(200_000, 100_000 * threads)))
-            reads_np = host_sample[:sample * READ_LEN].reshape(sample, READ_LEN)
-            r = cpu_reference_run(base, reads_np, threads, 2)
+            sample = args.cpu_sample or int(min(nq, max(200_000, 100_000 * threads) * per_read_scale))
+            offs_np = host_offs[:sample + 1].astype(np.int64)
+            flat_np = host_reads[:int(offs_np[-1])]
+            r = cpu_reference_run(base, flat_np, offs_np, threads, 2)
             if r is not None:
                 cpu = {"value": sample / r["passes"][-1], "unit": "reads/s", "cores": threads, "kind": "reference",
                        "sample": f"first {sample} reads of the workload, reference hot path (database::query_host) "
                                  f"via oracle/_ref/mc_ref_harness, {threads} threads, 2nd of 2 passes; "
                                  f"db load {r['load_seconds']:.0f}s untimed"}
             else:
-                n = 20000
-                tsec = cpu_port_run(db, reads_np[:n])
+                n = int(20000 * per_read_scale)
+                tsec = cpu_port_run(db, flat_np, offs_np[:n + 1])
                 cpu = {"value": n / tsec, "unit": "reads/s", "cores": 1, "kind": "port",
                        "sample": f"first {n} reads of the workload, oracle/mc_oracle.c, 1 thread"}
         except Exception as ex:                                  # never lose the GPU numbers
@@ -462,7 +491,7 @@ def main():
                    "sample": f"failed: {type(ex).__name__}: {ex}"}
 
     if rank == 0:
-        out = {"metric": "reads_per_second_150bp", "value": value, "unit": "reads/s", "n_gpus": world,
+        out = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64", "data": "synthetic", "config": config,
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}

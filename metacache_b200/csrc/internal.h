@@ -62,14 +62,15 @@ struct QueryArgs {
     const uint64_t* tax_of_tgt;   // may be null
     uint32_t        n_tax;        // entries in tax_of_tgt
     uint32_t        nq, s, maxc;
+    uint32_t        nq_cap;       // capacity of one heavy queue (= the workspace's max_queries)
     TableView       table;
     mcb200_candidate* top;        // [nq][maxc]
     // all-hits output (optional)
     uint64_t*       allhits;      // null if not wanted
     const uint64_t* allhits_off;  // [nq+1] for this part
     // heavy-query machinery
-    uint32_t*       heavy_list;   // [nq] query ids that overflowed the warp kernel
-    uint32_t*       heavy_count;  // [2]: [0] = appended, [1] = consumed (work queue)
+    uint32_t*       heavy_list;   // [2][nq] query ids that overflowed the warp kernel / the small-tier CTA kernel
+    uint32_t*       heavy_count;  // [2][2]: [0] = appended, [1] = consumed (work queues)
     uint64_t*       scratch;      // global scratch for huge queries (entries of 8 B + 4 B)
     uint64_t        scratch_entries;
     unsigned long long* scratch_cursor;

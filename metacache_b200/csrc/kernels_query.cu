@@ -756,8 +756,11 @@ __device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
     }
 }
 
+// Two tiers share this kernel: tier 0 (small shared-memory lists, many CTAs per SM) takes the reads
+// the warp kernel passed on and forwards those whose list does not fit to the queue of tier 1 (one CTA
+// per SM, 192 KB list, global scratch beyond that).
 __global__ void __launch_bounds__(kHeavyThreads)
-query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
+query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_cap)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_base[kHeavyThreads + 1];
@@ -777,8 +780,10 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            const uint32_t i = atomicAdd(a.heavy_count + 1, 1u);
-            s_q = (i < *reinterpret_cast<volatile uint32_t*>(a.heavy_count)) ? a.heavy_list[i] : 0xFFFFFFFFu;
+            const uint32_t* list = a.heavy_list + size_t(tier) * nq_cap;
+            uint32_t* count = a.heavy_count + 2 * tier;
+            const uint32_t i = atomicAdd(count + 1, 1u);
+            s_q = (i < *reinterpret_cast<volatile uint32_t*>(count)) ? list[i] : 0xFFFFFFFFu;
         }
         __syncthreads();
         const uint32_t q = s_q;
@@ -803,7 +808,10 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
 
         uint64_t* keys; uint32_t* cnt;
         if (n <= cap_smem) { keys = sh_keys; cnt = sh_cnt; }
-        else {
+        else if (tier == 0) {                          // too long for the small tier: next queue
+            if (tid == 0) a.heavy_list[size_t(nq_cap) + atomicAdd(a.heavy_count + 2, 1u)] = q;
+            continue;
+        } else {
             if (tid == 0) s_goff = atomicAdd(a.scratch_cursor, (unsigned long long)n);
             __syncthreads();
             const unsigned long long off = s_goff;
@@ -913,7 +921,8 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem)
     }
 }
 
-constexpr uint32_t kHeavySmemEntries = 16384;   // 16384 * 12 B = 192 KB
+constexpr uint32_t kHeavySmemEntries  = 16384;   // tier 1: 16384 * 12 B = 192 KB, one CTA per SM
+constexpr uint32_t kHeavySmallEntries = 2048;    // tier 0: 24 KB, up to 8 CTAs per SM
 
 void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
 {
@@ -923,8 +932,9 @@ void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
         cudaFuncSetAttribute(query_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr_set = true;
     }
-    query_heavy_kernel<<<sm_count, kHeavyThreads, smem, st>>>(a, kHeavySmemEntries);
-    count_launch();
+    query_heavy_kernel<<<sm_count * 8, kHeavyThreads, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, a.nq_cap);
+    query_heavy_kernel<<<sm_count, kHeavyThreads, smem, st>>>(a, kHeavySmemEntries, 1, a.nq_cap);
+    count_launch(2);
 }
 
 // ---------------------------------------------------------------------------

@@ -154,7 +154,7 @@ def make_targets(n_targets: int, target_len: int, family: int = 10, seed: int = 
 
 
 def _reads_chunk(B, lut, comp, targets, n_targets, target_len, i0, i1, read_len, seed, sub_thresh,
-                 n_thresh, frac_random_65536, device=None):
+                 n_thresh, frac_random_65536, device=None, pos_bits=12):
     n = i1 - i0
     idx = B.arange(n, device) + B.u(i0)
     h = B.sm(idx + B.u(_mix_seed(seed, 3)))
@@ -177,7 +177,7 @@ def _reads_chunk(B, lut, comp, targets, n_targets, target_len, i0, i1, read_len,
         raw = targets[src.astype(np.int64)]
         base = np.where(fwd, raw, comp[raw])
         codes = lut[base].astype(np.uint64)
-    hb = B.sm((idx[:, None] << (12 if B is _T else np.uint64(12))) + j[None, :] + B.u(_mix_seed(seed, 5)))
+    hb = B.sm((idx[:, None] << (pos_bits if B is _T else np.uint64(pos_bits))) + j[None, :] + B.u(_mix_seed(seed, 5)))
     rnd = B.shr(hb, 48) & (3 if B is _T else np.uint64(3))
     codes = B.where(is_random[:, None], rnd, _mutate(B, codes, hb, sub_thresh))
     isn = (B.shr(hb, 32) & (0xFFFF if B is _T else np.uint64(0xFFFF))) < (n_thresh if B is _T else np.uint64(n_thresh))
@@ -214,6 +214,82 @@ def make_reads_150(n_reads: int, targets, n_targets: int, target_len: int, read_
         o[isn] = ord("N")
         out[i0:i1] = o
     return out
+
+
+def make_long_reads(n_reads: int, targets, n_targets: int, target_len: int, seed: int = SEED_RLONG,
+                    sub_thresh: int = SUB_5PCT, device=None, max_len: int = 19000):
+    """RLONG recipe: reads of long_read_lengths(n_reads, seed) bases sampled from the targets with ~5 %
+    substitutions (no random reads, ~0.1 % N).  -> (uint8 bases back to back, int64 offsets [n_reads+1]).
+    Reads are generated per length class (cap = 256, 512, ... bases) at the cap length and cut to their
+    own length, so a read is reproducible from (seed, index, length).  torch device or numpy (None)."""
+    lens = np.minimum(long_read_lengths(n_reads, seed), min(max_len, target_len))
+    offs = np.zeros(n_reads + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    caps = 1 << np.ceil(np.log2(np.maximum(lens, 256))).astype(np.int64)
+    caps = np.minimum(caps, min(max_len, target_len))
+    if device is None:
+        out = np.empty(int(offs[-1]), np.uint8)
+        lut = np.zeros(256, np.uint8)
+        lut[_ASCII] = np.arange(4, dtype=np.uint8)
+        comp = np.arange(256, dtype=np.uint8)
+        comp[_ASCII] = _ASCII[::-1]
+    else:
+        import torch
+        out = torch.empty(int(offs[-1]), dtype=torch.uint8, device=device)
+        lut = torch.zeros(256, dtype=torch.uint8, device=device)
+        asc = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+        lut[asc.long()] = torch.arange(4, dtype=torch.uint8, device=device)
+        comp = torch.arange(256, dtype=torch.uint8, device=device)
+        comp[asc.long()] = asc.flip(0)
+    for cap in (int(c) for c in np.unique(caps)):
+        ids = np.nonzero(caps == cap)[0]
+        grp_size = max(1, min(4096, (1 << 24) // cap))
+        for b in range(0, len(ids), grp_size):
+            grp = ids[b:b + grp_size]
+            if device is None:
+                for i in grp:
+                    c, isn = _reads_chunk(_NP, lut, comp, targets, n_targets, target_len, int(i), int(i) + 1, cap,
+                                          seed, sub_thresh, N_01PCT, 0, None, 15)
+                    r = _ASCII[c.astype(np.int64)]
+                    r[isn] = ord("N")
+                    out[offs[i]:offs[i + 1]] = r[0, :lens[i]]
+            else:
+                idx = torch.as_tensor(grp, dtype=torch.int64, device=device)
+                c, isn = _reads_rows(_T, lut, comp, targets, n_targets, target_len, idx, cap, seed, sub_thresh,
+                                     N_01PCT, device, 15)
+                o = asc[c]
+                o[isn] = ord("N")
+                ln = torch.as_tensor(lens[grp], device=device)
+                keep = torch.arange(cap, device=device)[None, :] < ln[:, None]
+                out[_ragged_index(torch.as_tensor(offs[grp], device=device), cap, keep)] = o[keep]
+    return out, (offs if device is None else torch.as_tensor(offs, device=device))
+
+
+def _ragged_index(starts, cap, keep):
+    import torch
+    pos = starts[:, None] + torch.arange(cap, device=starts.device)[None, :]
+    return pos[keep]
+
+
+def _reads_rows(B, lut, comp, targets, n_targets, target_len, idx, read_len, seed, sub_thresh, n_thresh,
+                device, pos_bits):
+    """_reads_chunk for an arbitrary index vector (torch), no random reads"""
+    h = B.sm(idx + B.u(_mix_seed(seed, 3)))
+    strand = B.shr(h, 16) & 1
+    h1 = B.sm(idx + B.u(_mix_seed(seed, 4)))
+    tgt = B.mod(B.shr(h1, 1), n_targets)
+    off = B.mod(B.shr(B.sm(h1), 1), target_len - read_len + 1)
+    j = B.arange(read_len, device)
+    fwd = strand[:, None] == 0
+    rel = B.where(fwd, j[None, :] + 0 * off[:, None], (read_len - 1) - j[None, :] + 0 * off[:, None])
+    src = tgt[:, None] * target_len + off[:, None] + rel
+    raw = targets[src]
+    base = B.where(fwd, raw, comp[raw.long()])
+    codes = lut[base.long()].long()
+    hb = B.sm((idx[:, None] << pos_bits) + j[None, :] + B.u(_mix_seed(seed, 5)))
+    codes = _mutate(B, codes, hb, sub_thresh)
+    isn = (B.shr(hb, 32) & 0xFFFF) < n_thresh
+    return codes, isn
 
 
 def long_read_lengths(n_reads: int, seed: int = SEED_RLONG) -> np.ndarray:

@@ -138,3 +138,56 @@ def test_full_scale_c2_properties():
     h = (top[:, 0, 1] >= 5)
     assert 0.85 < h.mean() < 0.95
     db.close()
+
+
+def test_long_reads_c3_properties_and_oracle_sample():
+    """BASELINE config C3 (long reads, 200-19000 bp) at reduced size: reads of every length class go
+    through the fused kernel (<= 8 windows per range), the CTA kernel (longer) or its global-memory
+    variant; a seeded sample incl. the longest reads is compared bit-exactly with the oracle."""
+    import torch
+    from metacache_b200 import _lib, synth
+    from metacache_b200._lib import DevQueries, Sketching
+    from oracle import mc_oracle as O
+    device = torch.device("cuda", 0)
+    NT, TL, NQ = 2000, 100_000, 60_000
+    db, bases = _build(NT, TL, device)
+    flat, offs = synth.make_long_reads(NQ, bases, NT, TL, device=device)
+    lens = (offs[1:] - offs[:-1])
+    L = _lib.lib()
+    n_bases = int(offs[-1].item())
+    seq_off = offs.to(torch.int32)
+    seq_qry = torch.arange(NQ, dtype=torch.int32, device=device)
+    max_win = (2 + lens // 112).to(torch.int32)
+    ws = _lib.check_ptr(L.mcb200_workspace_create(db._h, NQ, NQ, n_bases + 64, MAXC, 0))
+    q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), NQ, NQ, n_bases)
+    sk = Sketching(**SK)
+    top_d = torch.empty((NQ, MAXC, 4), dtype=torch.int32, device=device)
+    _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top_d.data_ptr(), None))
+    torch.cuda.synchronize(device)
+    cnt = (C.c_uint64 * 8)()
+    _lib.check(L.mcb200_workspace_counters(ws, cnt))
+    top = top_d.cpu().numpy().view(np.uint32)
+    L.mcb200_workspace_destroy(ws)
+
+    hits = top[:, :, 1].astype(np.int64)
+    used = hits > 0
+    lens_np = lens.cpu().numpy()
+    W = 2 + lens_np // 112
+    assert np.all(hits[:, 0] >= hits[:, 1]) and np.all(~used[:, 1] | used[:, 0])
+    assert np.all(top[:, :, 0][used] < NT)
+    span = (top[:, :, 3].astype(np.int64) - top[:, :, 2].astype(np.int64))
+    assert np.all(span[used] >= 0) and np.all((span < W[:, None])[used])
+    both = used[:, 0] & used[:, 1]
+    assert np.all(top[both, 0, 0] != top[both, 1, 0])
+    assert (hits[:, 0] >= 5).mean() > 0.95                       # every long read comes from the database
+
+    keys, sizes, values = db.export_part(0)
+    tab = O.Table(keys, sizes, values)
+    flat_np, offs_np = flat.cpu().numpy(), offs.cpu().numpy()
+    rng = np.random.default_rng(12)
+    sample = set(int(i) for i in rng.choice(NQ, 1500, replace=False)) | set(int(i) for i in np.argsort(-lens_np)[:40])
+    for i in sorted(sample):
+        _, want = O.query(tab, flat_np[offs_np[i]:offs_np[i + 1]].tobytes(), b"")
+        got = [tuple(int(x) for x in row) for row in top[i] if row[1] > 0]
+        assert got == want, (i, int(lens_np[i]))
+    db.close()
