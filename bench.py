@@ -363,6 +363,7 @@ def main():
     calls = float(args.steps)
     n_launch = calls * world                                   # fused-kernel launches in the timed region
     feats_probed, locs, sectors = cnt[4] / n_launch, cnt[3] / n_launch, cnt[5] / n_launch
+    list_lines = cnt[6] / n_launch
     alg_bytes = 4 * SK["sketchlen"] * nwin_launch + 16 * feats_probed + 8 * locs + 16 * MAXC * nq + 8 * nq
     k_ms = (stage[3] + stage[4]) / n_launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -387,6 +388,14 @@ def main():
                 "sketch_kernel": {"alg_bytes": int(0.375 * n_bases + 4 * SK["sketchlen"] * nwin_launch),
                                   "achieved": round((0.375 * n_bases + 64 * nwin_launch) / max(stage[2] / calls, 1e-6) / 1e6, 1),
                                   "unit": "GB/s"},
+                # what the memory system allows for this access pattern: every table bucket and every 64-byte line of a
+                # location list is an isolated access = one HBM line activation; profiles/gather_bench_r1.log measures
+                # how many of those the B200 serves per second (independent 32-byte requests over a 16 GB working set)
+                "random_access": (lambda lines, rate: {
+                    "lines_per_read": round(lines / nq, 2), "measured_lines_per_s": rate,
+                    "floor_ms_per_launch": round(lines / rate * 1e3, 3),
+                    "frac_of_floor": round((lines / rate * 1e3) / k_ms, 4) if k_ms > 0 else None,
+                    "source": "profiles/gather_bench_r1.log (granule 32 B, 16 GB working set)"})(sectors + list_lines, 43.45e9),
                 "queries_fused_warp": int(cnt[0] / n_launch), "queries_cta_smem": int(cnt[1] / n_launch),
                 "queries_cta_global": int(cnt[2] / n_launch)}
 

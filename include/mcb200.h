@@ -269,7 +269,8 @@ const uint64_t* mcb200_workspace_allhits_offsets (const mcb200_workspace* ws); /
 /* counters of the last query call (host values; syncs the stream):
  * [0] queries handled by the fused warp kernel, [1] by the CTA kernel,
  * [2] by the global-memory kernel, [3] total locations gathered,
- * [4] total features probed, [5] total table buckets (32 B) read             */
+ * [4] total features probed, [5] total table buckets (32 B) read,
+ * [6] 64-byte lines of location lists fetched by the fused warp kernel       */
 int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8]);
 /* per-stage device times of the last calls, CUDA events on the caller's stream
  * (enable first): ms = [encode, window tables, sketch, fused probe+reduce warp

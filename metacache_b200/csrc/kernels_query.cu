@@ -169,17 +169,19 @@ __device__ __forceinline__ uint64_t warp_sort32 (uint64_t key) {
 
 // statistics (only when profiling is enabled): one set of REDs per warp, no CTA barrier
 __device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint32_t H,
-                                            uint32_t nfeat, uint32_t sectors)
+                                            uint32_t nfeat, uint32_t sectors, uint32_t list_lines = 0)
 {
     if (!a.counters) return;
     const uint32_t sec = __reduce_add_sync(kFull, sectors);
     const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
+    const uint32_t ll  = __reduce_add_sync(kFull, list_lines);
     if (lane_id() == 0) {
-        // counters: [0] fused queries [3] locations [4] features [5] sectors
+        // counters: [0] fused queries [3] locations [4] features [5] sectors [6] 64-byte lines of location lists
         unsigned long long* c = a.counters + ((blockIdx.x * kQWarps + (threadIdx.x >> 5)) % kCounterSlots) * 8;
         if (fused) { atomicAdd(c + 0, 1ull); atomicAdd(c + 3, (unsigned long long)H); }
         atomicAdd(c + 4, (unsigned long long)nf);
         atomicAdd(c + 5, (unsigned long long)sec);
+        atomicAdd(c + 6, (unsigned long long)ll);
     }
 }
 
@@ -318,7 +320,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
     const uint32_t W = __ldg(a.max_win + q);
     mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
-    uint32_t sectors = 0, nfeat = 0, H = 0, D = 0;
+    uint32_t sectors = 0, nfeat = 0, H = 0, D = 0, list_lines = 0;
 
     if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
@@ -333,6 +335,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
         uint32_t size = 0; uint64_t data = 0;
         if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
+        if (size > icap) list_lines += (size * uint32_t(sizeof(K)) + 63u) / 64u;
         const uint32_t incl = warp_incl_scan(size);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         if (total == 0) continue;
@@ -474,7 +477,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
         const uint32_t slot = list[j];
         hkeys[slot] = AK::kEmpty; hcnt[slot] = 0;
     }
-    warp_stats(a, ok, ok ? H : 0, nfeat, sectors);
+    warp_stats(a, ok, ok ? H : 0, nfeat, sectors, list_lines);
     __syncwarp();
     }
 }

@@ -369,14 +369,14 @@ __global__ void __launch_bounds__(kFastThreads)
 sketch_fast_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restrict__ amb,
                     const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_win_off,
                     const uint32_t* __restrict__ win_seq, const uint32_t* __restrict__ d_nwin,
-                    SketchParams p, uint32_t* __restrict__ feats, uint32_t stage_bases)
+                    SketchParams p, uint32_t* __restrict__ feats, uint32_t stage_bases, uint32_t nstages)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // [stage0 codes][stage1 codes][stage0 amb][stage1 amb][desc0][desc1][cand 32 x 129][redo 256][n_redo, base0, base1][bars]
     uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_amb   = s_codes + 2 * (stage_bases / 16);
-    WinDesc*  s_desc  = reinterpret_cast<WinDesc*>(s_amb + 2 * (stage_bases / 32));
-    uint32_t* s_cand  = reinterpret_cast<uint32_t*>(s_desc + 2 * kFastTile);
+    uint32_t* s_amb   = s_codes + nstages * (stage_bases / 16);
+    WinDesc*  s_desc  = reinterpret_cast<WinDesc*>(s_amb + nstages * (stage_bases / 32));
+    uint32_t* s_cand  = reinterpret_cast<uint32_t*>(s_desc + nstages * kFastTile);
     uint32_t* s_redo  = s_cand + 32 * kCandStride;
     uint32_t* s_misc  = s_redo + kFastTile;             // [0] windows to redo, [1..2] first base of a stage
     uint32_t* s_base  = s_misc + 1;
@@ -419,19 +419,30 @@ sketch_fast_kernel (const uint32_t* __restrict__ codes, const uint32_t* __restri
     const uint32_t rcsh = 2 * k - 2;
     uint32_t* mycand = s_cand + tid;
 
+    // nstages == 2: the copy of the next tile runs under the math of this one; nstages == 1: one
+    // staging buffer, more resident CTAs, the other CTAs of the SM cover the copy
     uint32_t tile = blockIdx.x;
-    if (tile < ntiles) {
+    if (nstages == 2 && tile < ntiles) {
         make_desc(tile, 0);
         __syncthreads();
         if (tid == 0) issue_copy(tile, 0);
     }
     for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t cur = it & 1u, nxt = cur ^ 1u;
-        const uint32_t next_tile = tile + gridDim.x;
-        if (next_tile < ntiles) make_desc(next_tile, nxt);
-        __syncthreads();
-        if (tid == 0 && next_tile < ntiles) issue_copy(next_tile, nxt);
-        mbar_wait(&s_bar[cur], (it >> 1) & 1u);
+        uint32_t cur = 0;
+        if (nstages == 2) {
+            cur = it & 1u;
+            const uint32_t nxt = cur ^ 1u;
+            const uint32_t next_tile = tile + gridDim.x;
+            if (next_tile < ntiles) make_desc(next_tile, nxt);
+            __syncthreads();
+            if (tid == 0 && next_tile < ntiles) issue_copy(next_tile, nxt);
+            mbar_wait(&s_bar[cur], (it >> 1) & 1u);
+        } else {
+            make_desc(tile, 0);
+            __syncthreads();
+            if (tid == 0) issue_copy(tile, 0);
+            mbar_wait(&s_bar[0], it & 1u);
+        }
 
         const uint32_t* sc = s_codes + cur * (stage_bases / 16);
         const uint32_t* sa = s_amb + cur * (stage_bases / 32);
@@ -541,14 +552,15 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
     if (p.w <= kFastMaxWin && p.s <= kFastMaxS && !no_fast) {
         uint32_t stage_bases = kFastTile * p.w + kAlignBases + kSlackBases + kAlignBases;
         stage_bases = (stage_bases + kAlignBases - 1) & ~(kAlignBases - 1);
-        const size_t smem = 2 * (stage_bases / 4) + 2 * (stage_bases / 8) + 2 * kFastTile * sizeof(WinDesc)
+        static const uint32_t nstages = [] { const char* e = getenv("MCB200_SKETCH_STAGES"); return (e && atoi(e) == 2) ? 2u : 1u; }();
+        const size_t smem = nstages * (stage_bases / 4) + nstages * (stage_bases / 8) + nstages * kFastTile * sizeof(WinDesc)
                           + 32 * kCandStride * 4 + kFastTile * 4 + 4 * sizeof(uint32_t) + 2 * sizeof(uint64_t);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_fast_kernel, int(kFastThreads), smem);
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2 * ctas_per_sm) per_sm = 2 * ctas_per_sm;
         sketch_fast_kernel<<<sm_count * per_sm, kFastThreads, smem, st>>>(codes, amb, seq_off, seq_win_off, win_seq,
-                                                                          d_nwin, p, feats, stage_bases);
+                                                                          d_nwin, p, feats, stage_bases, nstages);
         count_launch();
         return;
     }

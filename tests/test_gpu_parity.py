@@ -386,3 +386,45 @@ def test_classify_on_device_matches_oracle_with_synthetic_lineages(g1):
                 assert got == want, (i, frac, highest)
                 n_cls += 1
         assert n_cls > 300
+
+
+@pytest.mark.parametrize("k,s,w,stride", [
+    (16, 16, 127, 112),      # default geometry: thread-per-window kernel
+    (12, 8, 60, 49),         # short k-mers, short sketches (masked k-mer roll, scalar row store)
+    (16, 16, 256, 241),      # longest window the thread-per-window kernel stages
+    (9, 16, 300, 292),       # longer windows: warp-per-window kernel
+    (16, 32, 127, 112),      # sketches of 32 features: warp-per-window kernel
+    (16, 16, 40, 10),        # heavily overlapping windows, windows of <= 32 k-mers only
+])
+def test_sketch_geometries_against_oracle(g1, k, s, w, stride):
+    """window sketches for several (k, s, w, stride) vs the oracle's for_each_sketch restatement:
+    random reads with N runs, tandem repeats (duplicate k-mers inside a window), homopolymers,
+    reads shorter than k / w and lower case"""
+    from metacache_b200.database import SketchingOpt, query_reads
+    from oracle import mc_oracle as O
+    rng = np.random.default_rng(k * 1000 + w)
+    reads = []
+    for i in range(400):
+        n = int(rng.choice([1, 5, k - 1, k, k + 1, w - 1, w, w + 1, 150, 151, 333, 1000, 2500]))
+        r = rng.choice(list(b"ACGT"), n).astype(np.uint8)
+        kind = i % 8
+        if kind == 1 and n:
+            r[rng.integers(0, n, max(1, n // 50))] = ord("N")
+        elif kind == 2 and n > 40:
+            a = int(rng.integers(0, n - 20)); r[a:a + int(rng.integers(1, 40))] = ord("N")
+        elif kind == 3 and n:
+            unit = rng.choice(list(b"ACGT"), int(rng.integers(1, 7))).astype(np.uint8)
+            r = np.resize(unit, n)
+        elif kind == 4 and n:
+            r[:] = ord("A")
+        elif kind == 5:
+            r = np.frombuffer(bytes(r).lower(), np.uint8).copy()
+        reads.append(r.tobytes())
+    res = query_reads(g1.db, reads, SketchingOpt(k, s, w, stride), with_sketches=True, copy_all_hits=False)
+    for i, (seq, item) in enumerate(zip(reads, res)):
+        want = O.sketch_sequence(seq, k, s, w, stride)
+        got = item[2]
+        assert len(got) == len(want), (i, len(seq))
+        for j, (x, y) in enumerate(zip(got, want)):
+            y = np.zeros(0, np.uint32) if y is None else y
+            assert np.array_equal(x, y), (i, j, len(seq))
