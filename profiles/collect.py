@@ -95,13 +95,15 @@ def ncu_text(rep, out, lines_func=None, units=1e6):
 def main(tag):
     for log, name in (("bench_full.log", f"bench_{tag}.json"), ("bench_ref.log", f"bench_ref_{tag}.json"),
                       ("bench_n2.log", f"bench_n2_{tag}.json"), ("bench_n4.log", f"bench_n4_{tag}.json"),
-                      ("bench_n8.log", f"bench_n8_{tag}.json")):
+                      ("bench_n8.log", f"bench_n8_{tag}.json"), ("bench_c3.log", f"bench_c3_{tag}.json"),
+                      ("bench_ref_n2.log", f"bench_ref_n2_{tag}.json"), ("bench_ref_n4.log", f"bench_ref_n4_{tag}.json"),
+                      ("bench_ref_n8.log", f"bench_ref_n8_{tag}.json")):
         j = last_json(os.path.join(G, log))
         if j:
             json.dump(j, open(os.path.join(P, name), "w"), indent=1)
     launches(tag)
     ncu_text(f"prof_query_{tag}.ncu-rep", f"ncu_query_fast_{tag}", "_ZN3mcb17query_fast_kernelIjEEvNS_9QueryArgsEj", 1e6)
-    ncu_text(f"prof_sketch_{tag}.ncu-rep", f"ncu_sketch_{tag}", "_ZN3mcb13sketch_kernelEPKjS1_S1_S1_S1_S1_NS_12SketchParamsEPjjj", 2e6)
+    ncu_text(f"prof_sketch_{tag}.ncu-rep", f"ncu_sketch_{tag}", "_ZN3mcb18sketch_fast_kernelEPKjS1_S1_S1_S1_S1_NS_12SketchParamsEPjjj", 2e6)
     for f in ("gather_bench3.log", "exp1.log"):
         if os.path.exists(os.path.join(G, f)):
             dst = os.path.join(P, "gather_bench_" + tag + ".log") if f.startswith("gather") else os.path.join(P, "exp", f"exp1_{tag}.log")

@@ -8,14 +8,16 @@ nproc > gpurun_out/nproc.txt
 tail -3 gpurun_out/pytest_gpu.log
 ( timeout 600 python bench.py --impl reference 2>&1 | tail -1 ) > gpurun_out/bench_ref.log
 ( timeout 600 python bench.py 2>&1 | tail -1 ) > gpurun_out/bench_full.log
+( timeout 600 python bench.py --workload C3 2>&1 | tail -1 ) > gpurun_out/bench_c3.log
 cut -c1-600 gpurun_out/bench_ref.log; cut -c1-1500 gpurun_out/bench_full.log
-K='regex:^(encode|count_windows|fill_windows|sketch|query_fast|query_warp|query_heavy|merge_candidates|count_hits|table_insert|classify)_kernel|DeviceScan'
+K='regex:^(encode|count_windows|fill_windows|sketch|sketch_fast|query_fast|query_warp|query_heavy|merge_candidates|count_hits|table_insert|classify)_kernel|DeviceScan'
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$K" -c 400 --csv \
     --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
 tail -c 200 gpurun_out/launches_bench.log
-# full captures on a 1 M-read launch of the same workload (the 4th launch of each kernel = after warm-up)
+# full captures on a 1 M-read launch of the same workload, after warm-up (the database build launches the
+# sketch kernel 5 times before the first query)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:query_fast_kernel -s 3 -c 1 -f -o gpurun_out/prof_query_r1 \
     python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_query.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sketch_kernel -s 3 -c 1 -f -o gpurun_out/prof_sketch_r1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sketch_fast_kernel -s 8 -c 1 -f -o gpurun_out/prof_sketch_r1 \
     python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_sketch.log 2>&1
 ls -la gpurun_out
