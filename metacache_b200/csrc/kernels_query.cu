@@ -30,7 +30,6 @@
 namespace mcb {
 
 constexpr int      kQWarps   = 8;           // warps per CTA in the fused kernel
-constexpr int      kHeavyThreads = 256;
 constexpr uint32_t kMaxCand  = 32;          // candidates per query supported on device
 constexpr uint32_t kCounterSlots = 64;      // counters are spread over 64 slots x 8
 
@@ -726,6 +725,7 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream
 // ---------------------------------------------------------------------------
 // heavy queries: one CTA per query, shared memory if it fits, else global scratch
 // ---------------------------------------------------------------------------
+template <int kHeavyThreads>
 __device__ __forceinline__ uint32_t block_excl_scan (uint32_t v, uint32_t* s_warp, uint32_t& total) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t incl = warp_incl_scan(v);
@@ -743,7 +743,7 @@ __device__ __forceinline__ uint32_t block_excl_scan (uint32_t v, uint32_t* s_war
     return woff + incl - v;
 }
 
-template <class KeyPtr>
+template <int kHeavyThreads, class KeyPtr>
 __device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -762,6 +762,7 @@ __device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
 // Two tiers share this kernel: tier 0 (small shared-memory lists, many CTAs per SM) takes the reads
 // the warp kernel passed on and forwards those whose list does not fit to the queue of tier 1 (one CTA
 // per SM, 192 KB list, global scratch beyond that).
+template <int kHeavyThreads>
 __global__ void __launch_bounds__(kHeavyThreads)
 query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_cap)
 {
@@ -805,7 +806,7 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
             if (f != kNoFeature) { uint64_t d; mysum += table_find(a.table, f, d, sectors); ++nfeat; }
         }
         uint32_t H = 0;
-        block_excl_scan(mysum, s_warp, H);
+        block_excl_scan<kHeavyThreads>(mysum, s_warp, H);
         if (H == 0) { if (tid == 0) write_empty(top, 0, a.maxc); continue; }
         const uint32_t n = max(pow2_ceil(H), 2u);
 
@@ -834,7 +835,7 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
             uint32_t size = 0; uint64_t data = 0;
             if (f != kNoFeature) { uint32_t sx = 0; size = table_find(a.table, f, data, sx); }
             uint32_t total = 0;
-            const uint32_t excl = block_excl_scan(size, s_warp, total);
+            const uint32_t excl = block_excl_scan<kHeavyThreads>(size, s_warp, total);
             s_base[tid] = filled + excl;
             s_data[tid] = data;
             if (tid == kHeavyThreads - 1) s_base[kHeavyThreads] = filled + total;
@@ -853,7 +854,7 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
         for (uint32_t i = H + tid; i < n; i += kHeavyThreads) keys[i] = kPadKey;
         __syncthreads();
 
-        block_bitonic_sort(keys, n);
+        block_bitonic_sort<kHeavyThreads>(keys, n);
 
         if (a.allhits) {
             uint64_t* dst = a.allhits + a.allhits_off[q];
@@ -926,17 +927,19 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
 
 constexpr uint32_t kHeavySmemEntries  = 16384;   // tier 1: 16384 * 12 B = 192 KB, one CTA per SM
 constexpr uint32_t kHeavySmallEntries = 2048;    // tier 0: 24 KB, up to 8 CTAs per SM
+constexpr int      kHeavySmall = 256;            // threads per CTA, tier 0
+constexpr int      kHeavyBig   = 1024;           // tier 1: the one CTA of an SM uses all its warp slots
 
 void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
 {
     static bool attr_set = false;
     const size_t smem = size_t(kHeavySmemEntries) * 12;
     if (!attr_set) {
-        cudaFuncSetAttribute(query_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr_set = true;
     }
-    query_heavy_kernel<<<sm_count * 8, kHeavyThreads, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, a.nq_cap);
-    query_heavy_kernel<<<sm_count, kHeavyThreads, smem, st>>>(a, kHeavySmemEntries, 1, a.nq_cap);
+    query_heavy_kernel<kHeavySmall><<<sm_count * 8, kHeavySmall, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, a.nq_cap);
+    query_heavy_kernel<kHeavyBig><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, a.nq_cap);
     count_launch(2);
 }
 
