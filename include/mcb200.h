@@ -285,6 +285,38 @@ int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap);
 /* number of kernel launches issued by this library in this process           */
 uint64_t mcb200_kernel_launches (void);
 
+/* ---- FASTA / FASTQ (+gz) input ----------------------------
+ * sequence_pair_reader(filename1, filename2) (sequence_io.cpp:253-275): record
+ * grammar of sequence_reader::read_next (sequence_io.cpp:157-226).  filename2
+ * NULL or "" = unpaired; == filename1 = pairs of consecutive sequences of one
+ * file (-pairseq); else two files read in lockstep (-pairfiles).  gzip input is
+ * detected by its magic bytes.  A reader is NOT thread safe; use one per thread. */
+typedef struct mcb200_reader mcb200_reader;
+mcb200_reader* mcb200_reader_open  (const char* filename1, const char* filename2);
+/* unpaired reader over the records that START in [byte_begin, byte_end) of an
+ * uncompressed file: disjoint ranges give disjoint record sets, so one reader
+ * per host thread replaces the reference's single reader thread
+ * (database_query.hpp:257-281).  FASTQ ranges assume one sequence line per record. */
+mcb200_reader* mcb200_reader_open_range (const char* filename, uint64_t byte_begin, uint64_t byte_end);
+void     mcb200_reader_close (mcb200_reader* r);
+uint64_t mcb200_reader_index (const mcb200_reader* r);      /* queries delivered so far */
+/* sequence_pair_reader::next: 1 = a query (pointers valid until the next call on
+ * this reader; header without '>' / '@'; seq2 / len2 = mate, 0 if unpaired), 0 = end */
+int mcb200_reader_next (mcb200_reader* r, const char** header, uint64_t* header_len,
+                        const char** seq1, uint64_t* len1, const char** seq2, uint64_t* len2);
+/* sequence_pair_reader::skip (sequence_io.cpp): parses and drops up to n queries; *bases = their
+ * sequence characters.  Returns the number skipped.                                            */
+int64_t mcb200_reader_skip (mcb200_reader* r, uint64_t n, uint64_t* bases);
+/* the reader-thread loop of query_batched fused with add_paired_read
+ * (query_batch.cuh:85-186): parses up to max_reads queries straight into the
+ * pinned buffers of `slot`, with the candidate rules of
+ * make_candidate_generation_rules (candidate_structs.hpp:134-151).  Stops when the
+ * slot (or header_buf) is full; that query is delivered by the next call.
+ * header_buf / header_off ([max_reads + 1]) may be NULL.  Returns queries added.  */
+int64_t mcb200_reader_fill_batch (mcb200_reader* r, mcb200_batch* batch, uint32_t slot,
+                                  uint64_t insert_size_max, uint32_t winstride, uint32_t max_reads,
+                                  char* header_buf, uint64_t header_cap, uint64_t* header_off);
+
 #ifdef __cplusplus
 }
 #endif

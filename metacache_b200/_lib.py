@@ -68,6 +68,13 @@ _SIGS = {
     "mcb200_abi_version": (C.c_int, []),
     "mcb200_last_error": (C.c_char_p, []),
     "mcb200_device_count": (C.c_int, []),
+    "mcb200_reader_open": (_P, [C.c_char_p, C.c_char_p]),
+    "mcb200_reader_open_range": (_P, [C.c_char_p, C.c_uint64, C.c_uint64]),
+    "mcb200_reader_close": (None, [_P]),
+    "mcb200_reader_index": (C.c_uint64, [_P]),
+    "mcb200_reader_next": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "mcb200_reader_skip": (C.c_int64, [_P, C.c_uint64, _P]),
+    "mcb200_reader_fill_batch": (C.c_int64, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P]),
     "mcb200_db_open": (_P, [C.c_int, C.c_uint32]),
     "mcb200_db_close": (None, [_P]),
     "mcb200_db_part_begin": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float]),

@@ -98,6 +98,9 @@ struct mcb200_db {
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 };
 
+// for the host-only translation units of the library (reader.cpp)
+extern "C" int mcb200_internal_set_error (int code, const char* msg) { return fail(code, "%s", msg ? msg : ""); }
+
 static int use_device (int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

@@ -428,3 +428,53 @@ def test_sketch_geometries_against_oracle(g1, k, s, w, stride):
         for j, (x, y) in enumerate(zip(got, want)):
             y = np.zeros(0, np.uint32) if y is None else y
             assert np.array_equal(x, y), (i, j, len(seq))
+
+
+def _tops_of(top_rows):
+    return [tuple(int(x) for x in row) for row in top_rows if row[1] > 0]
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_query_file_matches_query_reads(g1, tmp_path, threads):
+    """file -> reader threads -> batch slots -> top hits (SURVEY 8f N2) == add_paired_read per read;
+    FASTA (wrapped lines), FASTQ and two paired files"""
+    from metacache_b200.database import query_reads
+    from metacache_b200.reader import query_file
+    sk = _sk(g1)
+    # single-end reads; FASTA cannot express an empty first line distinctly, so keep reads with characters
+    single = [a for a, b in g1.reads if len(a) > 0 and len(b) == 0]
+    want = [r[1] for r in query_reads(g1.db, single, sk, copy_all_hits=False)]
+    fa = tmp_path / "single.fa"
+    with open(fa, "wb") as f:
+        for i, s in enumerate(single):
+            f.write(b">read_%d some description\n" % i)
+            for p in range(0, len(s), 70):
+                f.write(s[p:p + 70] + b"\n")
+    top, heads = query_file(g1.db, str(fa), sketching=sk, threads=threads, batch_queries=37, keep_headers=True)
+    assert len(top) == len(single)
+    assert [h.decode() for h in heads] == ["read_%d some description" % i for i in range(len(single))]
+    assert [_tops_of(t) for t in top] == want
+    fq = tmp_path / "single.fq"
+    with open(fq, "wb") as f:
+        for i, s in enumerate(single):
+            f.write(b"@read_%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    top, _ = query_file(g1.db, str(fq), sketching=sk, threads=threads, batch_queries=1000)
+    assert [_tops_of(t) for t in top] == want
+    # pairs
+    pairs = [(a, b) for a, b in g1.reads if len(a) > 0 and len(b) > 0]
+    if pairs:
+        want_p = [r[1] for r in query_reads(g1.db, pairs, sk, copy_all_hits=False)]
+        f1, f2 = tmp_path / "p.1.fa", tmp_path / "p.2.fa"
+        with open(f1, "wb") as a, open(f2, "wb") as b:
+            for i, (x, y) in enumerate(pairs):
+                a.write(b">p%d/1\n" % i + x + b"\n")
+                b.write(b">p%d/2\n" % i + y + b"\n")
+        top, _ = query_file(g1.db, str(f1), str(f2), sketching=sk, threads=threads, batch_queries=50)
+        assert [_tops_of(t) for t in top] == want_p
+        # the same pairs interleaved in one file (-pairseq)
+        il = tmp_path / "p.il.fa"
+        with open(il, "wb") as f:
+            for i, (x, y) in enumerate(pairs):
+                f.write(b">p%d/1\n" % i + x + b"\n>p%d/2\n" % i + y + b"\n")
+        top, _ = query_file(g1.db, str(il), str(il), sketching=sk, threads=threads, batch_queries=50)
+        assert [_tops_of(t) for t in top] == want_p

@@ -1,0 +1,96 @@
+"""FASTA/FASTQ reader (csrc/reader.cpp) against the reference's own reader: the golden
+records in tests/golden/reader.json were produced by oracle/_ref/mc_ref_reader (ref_reader.cpp linked
+with the unmodified sequence_io.cpp) from the inputs in tests/reader_cases.py."""
+import gzip
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from metacache_b200._lib import Mcb200Error
+from metacache_b200.reader import SequenceReader
+from tests.reader_cases import CASES, big_content
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = {e["name"]: e for e in json.load(open(os.path.join(HERE, "golden", "reader.json")))}
+
+
+def _write(case, d):
+    paths = []
+    for i, (kind, data) in enumerate(case["files"]):
+        raw = big_content(data) if kind == "big" else data
+        if case.get("gz"):
+            raw = gzip.compress(raw)
+        p = os.path.join(d, f"{case['name']}_{i}" + (".gz" if case.get("gz") else ""))
+        open(p, "wb").write(raw)
+        paths.append(p)
+    if case.get("pairseq"):
+        paths = [paths[0], paths[0]]
+    return paths
+
+
+def _records(reader):
+    out = []
+    for h, a, b in reader:
+        out.append([reader.index(), h.decode("latin1"), a.decode("latin1"), b.decode("latin1")])
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reader_matches_reference_reader(case, tmp_path):
+    gold = GOLD[case["name"]]
+    paths = _write(case, str(tmp_path))
+    if "error" in gold:
+        with pytest.raises(Mcb200Error) as ei:
+            SequenceReader(*paths)
+        assert gold["error"] in str(ei.value)
+        return
+    with SequenceReader(*paths) as r:
+        recs = _records(r)
+    if "digest" in gold:
+        g = gold["digest"]
+        assert len(recs) == g["n"]
+        assert [len(x[2]) for x in recs[:50]] == g["lens"]
+        assert zlib.crc32(json.dumps(recs, separators=(",", ":")).encode()) & 0xFFFFFFFF == g["crc"]
+    else:
+        assert recs == gold["records"]
+
+
+@pytest.mark.parametrize("name", ["big_fasta_long_lines", "big_fasta_wrapped", "big_fastq", "fasta_simple",
+                                  "fastq_qual_starts_with_at", "fasta_no_final_newline"])
+@pytest.mark.parametrize("nranges", [2, 3, 7, 64])
+def test_byte_ranges_partition_the_records(name, nranges, tmp_path):
+    """readers over disjoint byte ranges deliver every record exactly once, in file order"""
+    case = next(c for c in CASES if c["name"] == name)
+    path = _write(case, str(tmp_path))[0]
+    with SequenceReader(path) as r:
+        whole = [(h, a) for h, a, _ in r]
+    size = os.path.getsize(path)
+    rng = np.random.default_rng(nranges)
+    cuts = sorted(set([0, size] + [int(x) for x in rng.integers(0, size + 1, nranges - 1)]))
+    got = []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        with SequenceReader(path, byte_range=(b, e)) as r:
+            got += [(h, a) for h, a, _ in r]
+    assert got == whole
+
+
+def test_bundled_reference_reads_if_present():
+    """the reads of the reference's own test suite (present where oracle/_ref/c1 was unpacked)"""
+    c1 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "c1")
+    if not os.path.exists(os.path.join(c1, "single.fa")):
+        pytest.skip("oracle/_ref/c1 not unpacked")
+    with SequenceReader(os.path.join(c1, "single.fa")) as r:
+        n = sum(1 for _ in r)
+    heads = sum(1 for line in open(os.path.join(c1, "single.fa"), "rb") if line.startswith(b">"))
+    assert n == heads and n > 1000
+    with SequenceReader(os.path.join(c1, "pair.1.fa"), os.path.join(c1, "pair.2.fa")) as r:
+        pairs = list(r)
+    assert all(len(a) and len(b) for _, a, b in pairs)
+
+
+def test_reader_errors():
+    with pytest.raises(Mcb200Error):
+        SequenceReader("/nonexistent/file.fa")
