@@ -28,6 +28,10 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <fstream>
+#include <exception>
 
 #include "../../include/mcb200.h"
 
@@ -315,6 +319,117 @@ void gpu_hashmap<Key, ValueT>::query_async (query_batch<ValueT>& batch, part_id 
     batch.host_data(hostId).lowest_rank(lowestRank);
     const mcb200_sketching s{sk.kmerlen, sk.sketchlen, sk.winlen, sk.winstride};
     if (mcb200_batch_submit(batch.handle(), hostId, &s)) throw_last("query_async");
+}
+
+//-----------------------------------------------------------------------------
+/** sequence_pair_reader (sequence_io.hpp:123-190) over mcb200_reader_*: same pairing
+ *  modes (filename2 empty = none, == filename1 = consecutive sequences, else lockstep
+ *  files), same record grammar.  Qualities are parsed but not kept. */
+class sequence_pair_reader
+{
+public:
+    using index_type = std::uint64_t;
+    struct sequence { index_type index = 0; std::string header; std::string data; };
+    using sequence_pair = std::pair<sequence, sequence>;
+
+    explicit sequence_pair_reader (const std::string& filename1, const std::string& filename2 = "")
+        : r_(mcb200_reader_open(filename1.c_str(), filename2.c_str())) { if (!r_) throw_last("sequence_pair_reader"); }
+    /** ours: only the records that start in [byteBegin, byteEnd) of an uncompressed, unpaired file */
+    sequence_pair_reader (const std::string& filename, std::uint64_t byteBegin, std::uint64_t byteEnd)
+        : r_(mcb200_reader_open_range(filename.c_str(), byteBegin, byteEnd)) { if (!r_) throw_last("sequence_pair_reader"); }
+    sequence_pair_reader (const sequence_pair_reader&) = delete;
+    sequence_pair_reader (sequence_pair_reader&& o) noexcept : r_(o.r_), ahead_(std::move(o.ahead_)), have_(o.have_) { o.r_ = nullptr; }
+    ~sequence_pair_reader () { if (r_) mcb200_reader_close(r_); }
+
+    bool has_next () { if (!have_) fetch(); return have_; }
+    sequence_pair next () { sequence_pair p; next(p); return p; }
+    void next (sequence_pair& p) { if (has_next()) { p = std::move(ahead_); have_ = false; } }
+    void skip (index_type n) {
+        if (n && have_) { have_ = false; --n; }
+        if (n && mcb200_reader_skip(r_, n, nullptr) < 0) throw_last("skip");
+    }
+    index_type index () const noexcept { return mcb200_reader_index(r_) - (have_ ? 1 : 0); }
+    mcb200_reader* handle () const noexcept { return have_ ? nullptr : r_; }   // raw access only without look-ahead
+
+private:
+    void fetch () {
+        const char *h, *a, *b; std::uint64_t hl, al, bl;
+        const int rc = mcb200_reader_next(r_, &h, &hl, &a, &al, &b, &bl);
+        if (rc < 0) throw_last("next");
+        have_ = rc == 1;
+        if (have_) {
+            ahead_.first.index = ahead_.second.index = mcb200_reader_index(r_);
+            ahead_.first.header.assign(h ? h : "", hl);
+            ahead_.first.data.assign(a ? a : "", al);
+            ahead_.second.header.clear();
+            ahead_.second.data.assign(b ? b : "", bl);
+        }
+    }
+    mcb200_reader* r_ = nullptr;
+    sequence_pair ahead_;
+    bool have_ = false;
+};
+
+//-----------------------------------------------------------------------------
+/** What `query_batched` (database_query.hpp:170-303) does with one reader thread and
+ *  N workers, with N reader+worker threads instead: each thread parses ITS byte range of
+ *  the file straight into the pinned buffers of its batch slot (mcb200_reader_fill_batch =
+ *  reader loop + add_paired_read), submits under the schedule mutex, waits, and hands the
+ *  slot's results to `consume(threadId, batchNo, headers, hostData)`.  Ranges are ordered,
+ *  so (threadId, batchNo) is file order.  Paired or gzip input runs on one thread. */
+template <class Location, class Consumer>
+void query_files (gpu_hashmap<feature, Location>& store, const std::string& file1, const std::string& file2,
+                  const sketching_opt& sk, std::uint32_t maxCandidates, std::uint64_t insertSizeMax,
+                  unsigned numThreads, std::uint32_t batchSize, bool keepHeaders, Consumer&& consume)
+{
+    bool ranged = file2.empty() && numThreads > 1;
+    std::uint64_t size = 0;
+    if (ranged) {
+        std::ifstream f(file1, std::ios::binary | std::ios::ate);
+        if (!f) throw std::runtime_error("can't open file " + file1);
+        size = std::uint64_t(f.tellg());
+        f.seekg(0);
+        unsigned char m[2] = {0, 0};
+        f.read(reinterpret_cast<char*>(m), 2);
+        if (m[0] == 0x1f && m[1] == 0x8b) ranged = false;          // gzip: no byte ranges
+    }
+    if (!ranged) numThreads = 1;
+    std::vector<mcb200_reader*> readers(numThreads, nullptr);
+    struct closer { std::vector<mcb200_reader*>& v; ~closer () { for (auto r : v) if (r) mcb200_reader_close(r); } } guard{readers};
+    for (unsigned t = 0; t < numThreads; ++t) {
+        readers[t] = ranged ? mcb200_reader_open_range(file1.c_str(), size * t / numThreads, size * (t + 1) / numThreads)
+                            : mcb200_reader_open(file1.c_str(), file2.c_str());
+        if (!readers[t]) throw_last("query_files");
+    }
+    query_batch<Location> batch(batchSize, std::max<std::uint32_t>(1u << 22, batchSize * 256u), sk.sketchlen,
+                                sk.sketchlen * 254, maxCandidates, false, part_id(numThreads), store.table_count(), 0, &store);
+    std::mutex scheduleMtx, consumeMtx;
+    std::exception_ptr error;
+    auto work = [&] (unsigned t) {
+        try {
+            std::vector<char> hbuf(keepHeaders ? std::size_t(batchSize) * 64 : 0);
+            std::vector<std::uint64_t> hoff(keepHeaders ? batchSize + 1 : 0);
+            auto& hd = batch.host_data(part_id(t));
+            for (std::uint64_t batchNo = 0; ; ++batchNo) {
+                const std::int64_t n = mcb200_reader_fill_batch(readers[t], batch.handle(), t, insertSizeMax, sk.winstride,
+                                                                batchSize, keepHeaders ? hbuf.data() : nullptr, hbuf.size(),
+                                                                keepHeaders ? hoff.data() : nullptr);
+                if (n < 0) throw_last("query_files");
+                if (n == 0) break;
+                { std::lock_guard<std::mutex> lock(scheduleMtx); store.query_async(batch, part_id(t), sk, 0); }
+                hd.wait_for_results();
+                std::vector<std::string> headers;
+                if (keepHeaders) for (std::int64_t i = 0; i < n; ++i) headers.emplace_back(hbuf.data() + hoff[i], hoff[i + 1] - hoff[i]);
+                { std::lock_guard<std::mutex> lock(consumeMtx); consume(t, batchNo, headers, hd); }
+                hd.clear();
+            }
+        } catch (...) { std::lock_guard<std::mutex> lock(consumeMtx); if (!error) error = std::current_exception(); }
+    };
+    std::vector<std::thread> threads;
+    for (unsigned t = 1; t < numThreads; ++t) threads.emplace_back(work, t);
+    work(0);
+    for (auto& th : threads) th.join();
+    if (error) std::rethrow_exception(error);
 }
 
 } // namespace mcb200

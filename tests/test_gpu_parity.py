@@ -478,3 +478,33 @@ def test_query_file_matches_query_reads(g1, tmp_path, threads):
                 f.write(b">p%d/1\n" % i + x + b"\n>p%d/2\n" % i + y + b"\n")
         top, _ = query_file(g1.db, str(il), str(il), sketching=sk, threads=threads, batch_queries=50)
         assert [_tops_of(t) for t in top] == want_p
+
+
+def test_cpp_query_files_driver(g1, tmp_path):
+    """metacache_b200/host/shim_query_file.cpp: mcb200::query_files (C++ reader + worker threads over
+    the C ABI, the query_batched replacement) on a FASTA file == add_paired_read per read"""
+    import subprocess
+    from metacache_b200 import dbformat
+    from metacache_b200.database import query_reads
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metacache_b200", "host")
+    exe = os.path.join(host, "shim_query_file")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", host])
+    dbp = str(tmp_path / "g1.cache0")
+    dbformat.write_cache(dbp, dbformat.CachePart(g1.keys, g1.sizes, g1.values))
+    single = [a for a, b in g1.reads if len(a) > 0 and len(b) == 0]
+    want = [r[1] for r in query_reads(g1.db, single, _sk(g1), copy_all_hits=False)]
+    fa = str(tmp_path / "single.fa")
+    with open(fa, "wb") as f:
+        for i, s in enumerate(single):
+            f.write(b">q%d\n" % i)
+            for p in range(0, len(s), 80):
+                f.write(s[p:p + 80] + b"\n")
+    for threads in ("1", "5"):
+        out = subprocess.run([exe, dbp, fa, "-", threads, "2"], check=True, capture_output=True, text=True).stdout.splitlines()
+        assert len(out) == len(single)
+        for i, line in enumerate(out):
+            head, tops = line.split("\t")
+            assert head == "q%d" % i
+            got = [tuple(int(x) for x in t.split(":")) for t in tops.split(",")] if tops else []
+            assert got == want[i], i
