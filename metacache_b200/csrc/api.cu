@@ -419,7 +419,7 @@ extern "C" mcb200_workspace* mcb200_workspace_create (mcb200_db* db, uint32_t ma
     ok(ws->codes.ensure(padded / 16 + 64)); ok(ws->amb.ensure(padded / 32 + 64));
     ok(ws->seq_nwin.ensure(max_seqs + 1)); ok(ws->seq_win_off.ensure(max_seqs + 2));
     ok(ws->qry_win_off.ensure(max_queries + 1));
-    ok(ws->heavy_list.ensure(2 * uint64_t(max_queries))); ok(ws->heavy_count.ensure(4));
+    ok(ws->heavy_list.ensure(3 * uint64_t(max_queries))); ok(ws->heavy_count.ensure(6));
     ok(ws->counters.ensure(64 * 8)); ok(ws->scratch_cursor.ensure(1)); ok(ws->error.ensure(1));
     if (e == cudaSuccess) e = cudaMemset(ws->codes.p, 0, ws->codes.n * 4);
     if (e == cudaSuccess) e = cudaMemset(ws->amb.p, 0xFF, ws->amb.n * 4);
@@ -550,7 +550,7 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
     if (ws->scratch_entries == 0) { int rc = ensure_scratch(ws, 1ull << 22); if (rc) return rc; }
     QueryArgs a = make_args(ws, part, d_top);
     if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
-    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 16, st));
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
     if (ws->profiling && !ws->ev) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
     const bool prof = ws->profiling && ws->ev && ws->ev->q.size() >= (size_t(part) + 1) * 3;
@@ -598,7 +598,7 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
     QueryArgs a = make_args(ws, part, d_top);
     ws->q = saved_q; ws->sk = saved_sk;
     a.feats = d_feats; a.qry_win_off = d_qry_win_off;
-    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 16, st));
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
     if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
     const bool prof = ws->profiling && ws->ev;

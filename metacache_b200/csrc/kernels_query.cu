@@ -224,6 +224,7 @@ template <> struct AggKey<uint64_t> {
 };
 
 constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk staged in shared memory
+constexpr uint32_t kSecondPassSlots = 1024;   // per-warp table of the second pass of the fused kernel
 
 template <class K>
 __host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
@@ -278,9 +279,11 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
     return !(__any_sync(kFull, failed) || D > dmax);
 }
 
+// in_queue < 0: all reads of the batch; else the reads of that overflow queue (a second pass with a
+// larger table).  Reads this pass cannot settle go to out_queue.
 template <class K>
 __global__ void __launch_bounds__(kQWarps * 32)
-query_fast_kernel (QueryArgs a, uint32_t T)
+query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
     using AK = AggKey<K>;
     constexpr uint32_t EPS = 32 / sizeof(K);                                   // locations per 32-byte sector
@@ -313,7 +316,12 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     // persistent warps: a warp keeps its shared-memory table and walks the reads with a grid
     // stride, so warp slots never idle behind the slowest read of a CTA
     const uint32_t nwarps = gridDim.x * kQWarps;
-    for (uint32_t q = blockIdx.x * kQWarps + warp; q < a.nq; q += nwarps) {
+    const uint32_t* in_list = (in_queue >= 0) ? a.heavy_list + size_t(in_queue) * a.nq_cap : nullptr;
+    const uint32_t n_in = (in_queue >= 0) ? a.heavy_count[2 * in_queue] : a.nq;
+    uint32_t* out_list = a.heavy_list + size_t(out_queue) * a.nq_cap;
+    uint32_t* out_count = a.heavy_count + 2 * out_queue;
+    for (uint32_t qi = blockIdx.x * kQWarps + warp; qi < n_in; qi += nwarps) {
+    const uint32_t q = in_list ? in_list[qi] : qi;
     const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
     const uint32_t nslots = (w1 - w0) * a.s;
     const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
@@ -322,7 +330,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     uint32_t sectors = 0, nfeat = 0, H = 0, D = 0, list_lines = 0;
 
     if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
-        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+        if (lane == 0) out_list[atomicAdd(out_count, 1u)] = q;
         warp_stats(a, false, 0, 0, 0);
         continue;
     }
@@ -468,7 +476,7 @@ query_fast_kernel (QueryArgs a, uint32_t T)
     } else if (ok) {
         if (lane == 0) write_empty(top, 0, a.maxc);
     } else {
-        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+        if (lane == 0) out_list[atomicAdd(out_count, 1u)] = q;
     }
     // ---- leave the table empty for the next read ----
     __syncwarp();
@@ -704,16 +712,23 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
     if (!a.tax_of_tgt && !a.allhits) {
         // top hits only at rank "sequence": the sort-free kernel
-        const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(T) : fast_smem_bytes<uint64_t>(T)) * kQWarps;
-        int per_sm = 0;
-        if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t>, kQWarps * 32, smem);
-        else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t>, kQWarps * 32, smem);
-        if (per_sm < 1) per_sm = 1;
+        // pass 0: every read, small per-warp tables, full occupancy; pass 1: the reads that overflowed them
+        // (queue 0), 1024-slot tables, 1-2 CTAs per SM; what is left (queue 1) goes to the CTA kernel
         static const int cap = [] { const char* e = getenv("MCB200_QUERY_CTAS"); return e ? atoi(e) : 0; }();
-        if (cap >= 1 && cap < per_sm) per_sm = cap;
-        const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
-        if (a.table.win_bits) query_fast_kernel<uint32_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);
-        else                  query_fast_kernel<uint64_t><<<pgrid, kQWarps * 32, smem, st>>>(a, T);
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t Tp = pass == 0 ? T : std::max<uint32_t>(T, kSecondPassSlots);
+            const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
+            int per_sm = 0;
+            if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t>, kQWarps * 32, smem);
+            else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t>, kQWarps * 32, smem);
+            if (per_sm < 1) per_sm = 1;
+            if (pass == 0 && cap >= 1 && cap < per_sm) per_sm = cap;
+            const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
+            const int in_queue = pass == 0 ? -1 : 0;
+            if (a.table.win_bits) query_fast_kernel<uint32_t><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            else                  query_fast_kernel<uint64_t><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            if (pass == 1) count_launch();
+        }
     } else {
         const size_t smem = warp_smem_bytes(T) * kQWarps;
         if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T);
@@ -764,7 +779,7 @@ __device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
 // per SM, 192 KB list, global scratch beyond that).
 template <int kHeavyThreads>
 __global__ void __launch_bounds__(kHeavyThreads)
-query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_cap)
+query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_queue, uint32_t nq_cap)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_base[kHeavyThreads + 1];
@@ -784,8 +799,8 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            const uint32_t* list = a.heavy_list + size_t(tier) * nq_cap;
-            uint32_t* count = a.heavy_count + 2 * tier;
+            const uint32_t* list = a.heavy_list + size_t(in_queue) * nq_cap;
+            uint32_t* count = a.heavy_count + 2 * in_queue;
             const uint32_t i = atomicAdd(count + 1, 1u);
             s_q = (i < *reinterpret_cast<volatile uint32_t*>(count)) ? list[i] : 0xFFFFFFFFu;
         }
@@ -813,7 +828,7 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t nq_c
         uint64_t* keys; uint32_t* cnt;
         if (n <= cap_smem) { keys = sh_keys; cnt = sh_cnt; }
         else if (tier == 0) {                          // too long for the small tier: next queue
-            if (tid == 0) a.heavy_list[size_t(nq_cap) + atomicAdd(a.heavy_count + 2, 1u)] = q;
+            if (tid == 0) a.heavy_list[size_t(in_queue + 1) * nq_cap + atomicAdd(a.heavy_count + 2 * (in_queue + 1), 1u)] = q;
             continue;
         } else {
             if (tid == 0) s_goff = atomicAdd(a.scratch_cursor, (unsigned long long)n);
@@ -938,8 +953,10 @@ void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
         cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr_set = true;
     }
-    query_heavy_kernel<kHeavySmall><<<sm_count * 8, kHeavySmall, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, a.nq_cap);
-    query_heavy_kernel<kHeavyBig><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, a.nq_cap);
+    // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
+    const uint32_t in_queue = (!a.tax_of_tgt && !a.allhits) ? 1u : 0u;
+    query_heavy_kernel<kHeavySmall><<<sm_count * 8, kHeavySmall, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);
+    query_heavy_kernel<kHeavyBig><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, in_queue + 1, a.nq_cap);
     count_launch(2);
 }
 
