@@ -209,6 +209,8 @@ template <> struct AggKey<uint32_t> {
     __device__ static __forceinline__ uint32_t win (uint32_t k, uint32_t wb) { return k & ((1u << wb) - 1u); }
     __device__ static __forceinline__ uint32_t tgt (uint32_t k, uint32_t wb) { return k >> wb; }
     __device__ static __forceinline__ uint32_t cas (uint32_t* p, uint32_t v) { return atomicCAS(p, kEmpty, v); }
+    // table key = location >> 1 = (tgt, pair of windows); index of that pair inside its target
+    __device__ static __forceinline__ uint32_t pair_index (uint32_t kb, uint32_t wb) { return kb & ((1u << (wb - 1)) - 1u); }
 };
 template <> struct AggKey<uint64_t> {
     static constexpr uint64_t kEmpty = ~0ull;
@@ -221,6 +223,7 @@ template <> struct AggKey<uint64_t> {
     __device__ static __forceinline__ uint64_t cas (uint64_t* p, uint64_t v) {
         return atomicCAS(reinterpret_cast<unsigned long long*>(p), kEmpty, v);
     }
+    __device__ static __forceinline__ uint32_t pair_index (uint64_t kb, uint32_t) { return uint32_t(kb) & 0x7FFFFFFFu; }
 };
 
 constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk staged in shared memory
@@ -254,8 +257,10 @@ __device__ __forceinline__ void load_sector (const void* p, uint32_t (&r)[8]) {
                  : "l"(p));
 }
 
-// One wave of <= 32 locations (one per lane, `active` lanes) into the per-warp table; slots that
-// were empty are appended to `list` (D of them so far).  Returns false if the table is too full.
+// One wave of <= 32 locations (one per lane, `active` lanes) into the per-warp table.  A table entry
+// is a PAIR of consecutive windows of a target (key = location >> 1) with two 16-bit multiplicities,
+// so that the window-range sums below need half the lookups.  Slots that were empty are appended to
+// `list` (D of them so far).  Returns false if the table is too full.
 template <class K>
 __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* list, uint32_t mask, uint32_t dmax,
                                           bool active, K v, uint32_t& D)
@@ -263,13 +268,15 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
     bool isnew = false, failed = false;
     uint32_t h = 0;
     if (active) {
-        h = AggKey<K>::hash(v) & mask;
+        const K kb = v >> 1;
+        const uint32_t one = 1u << (16u * (uint32_t(v) & 1u));
+        h = AggKey<K>::hash(kb) & mask;
         failed = true;
         #pragma unroll 1
         for (uint32_t probes = 0; probes < kMaxProbe; ++probes) {
-            const K old = AggKey<K>::cas(hkeys + h, v);
+            const K old = AggKey<K>::cas(hkeys + h, kb);
             isnew = (old == AggKey<K>::kEmpty);
-            if (isnew || old == v) { atomicAdd(hcnt + h, 1u); failed = false; break; }
+            if (isnew || old == kb) { atomicAdd(hcnt + h, one); failed = false; break; }
             h = (h + 1) & mask;
         }
     }
@@ -418,16 +425,29 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     }
 
     if (ok && H != 0) {
-        // ---- hits(j) per distinct location; lane-local best and best of another target ----
-        // order: (hits desc, location asc)
+        // ---- hits of the window ranges ending at the (one or two) windows of every table entry;
+        //      lane-local best and best of another target; order: (hits desc, location asc) ----
         uint32_t c1 = 0, c2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
         for (uint32_t j = lane; j < D; j += 32) {
             const uint32_t slot = list[j];
-            const K k = hkeys[slot];
-            uint32_t c = hcnt[slot];
-            const uint32_t win = AK::win(k, wb);
-            for (uint32_t d = 1; d < W && d <= win; ++d) c += agg_lookup<K>(hkeys, hcnt, mask, K(k - d));
-            hits[j] = c;
+            const K kb = hkeys[slot];
+            const uint32_t cnt = hcnt[slot];
+            const uint32_t n0 = cnt & 0xFFFFu, n1 = cnt >> 16;
+            uint32_t h0 = n0, h1 = n1 + (W > 1 ? n0 : 0u);
+            const uint32_t pidx = AK::pair_index(kb, wb);
+            // pair b-i holds the windows at distance 2i-1, 2i (from the even window) and 2i, 2i+1 (from the odd one)
+            for (uint32_t i = 1; 2 * i - 1 < W && i <= pidx; ++i) {
+                const uint32_t x = agg_lookup<K>(hkeys, hcnt, mask, K(kb - i));
+                const uint32_t lo = x & 0xFFFFu, hi = x >> 16;
+                h0 += hi;
+                if (2 * i < W) { h0 += lo; h1 += hi; }
+                if (2 * i + 1 < W) h1 += lo;
+            }
+            // the entry's candidate: more hits, the even (smaller) window on ties; a window without locations ends no range
+            const bool odd = (n1 != 0) && (n0 == 0 || h1 > h0);
+            const uint32_t c = odd ? h1 : h0;
+            const K k = K((kb << 1) | K(odd));
+            hits[j] = (c << 1) | uint32_t(odd);
             if (c > c1 || (c == c1 && k < k1)) {
                 if (c1 != 0 && AK::tgt(k1, wb) != AK::tgt(k, wb)) { c2 = c1; k2 = k1; }
                 c1 = c; k1 = k;
@@ -444,11 +464,12 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
             } else if (c > 1) {
                 best_c = 0; best_k = AK::kEmpty;
                 for (uint32_t j = lane; j < D; j += 32) {
-                    const K k = hkeys[list[j]];
+                    const uint32_t e = hits[j];
+                    const K k = K((hkeys[list[j]] << 1) | K(e & 1u));
                     const uint32_t tgt = AK::tgt(k, wb);
                     bool taken = false;
                     for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
-                    const uint32_t cj = hits[j];
+                    const uint32_t cj = e >> 1;
                     if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
                 }
             }
@@ -464,8 +485,10 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
                 K ke;
                 if (sizeof(K) == 4) ke = K((wt << wb) | ww); else ke = K((uint64_t(wt) << 32) | ww);
                 uint32_t beg = ww;
-                for (uint32_t d = 1; d < W && d <= ww; ++d)
-                    if (agg_lookup<K>(hkeys, hcnt, mask, K(ke - d))) beg = ww - d;
+                for (uint32_t d = 1; d < W && d <= ww; ++d) {
+                    const K kd = K(ke - d);
+                    if ((agg_lookup<K>(hkeys, hcnt, mask, K(kd >> 1)) >> (16u * (uint32_t(kd) & 1u))) & 0xFFFFu) beg = ww - d;
+                }
                 top[c] = mcb200_candidate{wt, wmax, beg, ww};
                 chosen[c] = wt;
             }
