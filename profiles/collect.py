@@ -86,6 +86,10 @@ def ncu_text(rep, out, lines_func=None, units=1e6):
         cubin = "kernels_query.sm_100a.cubin" if "query" in lines_func else "kernels_sketch.sm_100a.cubin"
         sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(cub, cubin)], capture_output=True, text=True).stdout
         open(os.path.join(cub, "all.sass"), "w").write(sass)
+        # lines_func is a prefix of the mangled name (the parameter list changes with the kernel's signature)
+        m = re.search(r"^\.text\.(" + re.escape(lines_func) + r"\w*):", sass, re.M)
+        if m:
+            lines_func = m.group(1)
         t = subprocess.run([sys.executable, os.path.join(P, "sass_lines.py"), tmp2, os.path.join(cub, "all.sass"),
                             lines_func, str(units), "40"], capture_output=True, text=True).stdout
         open(os.path.join(P, out.replace("ncu_", "ncu_lines_") + ".txt"), "w").write(
@@ -102,8 +106,8 @@ def main(tag):
         if j:
             json.dump(j, open(os.path.join(P, name), "w"), indent=1)
     launches(tag)
-    ncu_text(f"prof_query_{tag}.ncu-rep", f"ncu_query_fast_{tag}", "_ZN3mcb17query_fast_kernelIjEEvNS_9QueryArgsEj", 1e6)
-    ncu_text(f"prof_sketch_{tag}.ncu-rep", f"ncu_sketch_{tag}", "_ZN3mcb18sketch_fast_kernelEPKjS1_S1_S1_S1_S1_NS_12SketchParamsEPjjj", 2e6)
+    ncu_text(f"prof_query_{tag}.ncu-rep", f"ncu_query_fast_{tag}", "_ZN3mcb17query_fast_kernelIjEEvNS_9QueryArgsE", 1e6)
+    ncu_text(f"prof_sketch_{tag}.ncu-rep", f"ncu_sketch_{tag}", "_ZN3mcb18sketch_fast_kernelE", 2e6)
     for f in ("gather_bench3.log", "exp1.log"):
         if os.path.exists(os.path.join(G, f)):
             dst = os.path.join(P, "gather_bench_" + tag + ".log") if f.startswith("gather") else os.path.join(P, "exp", f"exp1_{tag}.log")

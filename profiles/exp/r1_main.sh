@@ -14,9 +14,10 @@ K='regex:^(encode|count_windows|fill_windows|sketch|sketch_fast|query_fast|query
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$K" -c 400 --csv \
     --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
 tail -c 200 gpurun_out/launches_bench.log
-# full captures on a 1 M-read launch of the same workload, after warm-up (the database build launches the
+# full captures on a 1 M-read launch of the same workload, after warm-up (the fused kernel runs two passes per
+# step: the 7th launch is the first pass of the 4th step; the database build launches the
 # sketch kernel 5 times before the first query)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:query_fast_kernel -s 3 -c 1 -f -o gpurun_out/prof_query_r1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:query_fast_kernel -s 6 -c 1 -f -o gpurun_out/prof_query_r1 \
     python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_query.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sketch_fast_kernel -s 8 -c 1 -f -o gpurun_out/prof_sketch_r1 \
     python bench.py --reads 1000000 --slot-reads 1000000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_sketch.log 2>&1
