@@ -72,7 +72,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -106,7 +106,7 @@ class ClockSampler:
             pass
         if sm:
             busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
-            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), samples=len(sm))
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), samples=len(busy), samples_total=len(sm))
         out["reasons"] = sorted(reasons)
         return out
 
@@ -341,7 +341,6 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop()
     launches = L.mcb200_kernel_launches() - launches0
     stage = (C.c_float * 8)()
     _lib.check(L.mcb200_workspace_stage_times(ws, stage))
@@ -475,6 +474,8 @@ def main():
         e2e = {"value": nq_total / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(n_bases * world),
                "d2h_bytes_per_step": int(nq * MAXC * 16 * world), "ms_per_step": round(e2e_ms, 3),
                "api": "pinned host reads -> H2D -> sketch/all-gather/probe/all-to-all/merge -> D2H"}
+
+    clk = clocks.stop()                                      # sampled through both timed regions (value and e2e)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
