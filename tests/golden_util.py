@@ -55,3 +55,21 @@ class G2:
 
 def kat():
     return np.load(os.path.join(GOLD, "kat.npz"))
+
+
+class G3:
+    """reference outputs for non-default sketching geometries (oracle/make_golden_geometry.py)"""
+
+    def __init__(self):
+        z = np.load(os.path.join(GOLD, "g3.npz"))
+        self.z = z
+        g1 = G1()
+        self.reads = [g1.reads[i] for i in z["read_index"]]
+        self.geometries = [tuple(int(x) for x in row) for row in z["geometries"]]
+
+    def part(self, gi):
+        z = self.z
+        return z[f"g{gi}_keys"], z[f"g{gi}_sizes"], z[f"g{gi}_values"]
+
+    def expected(self, gi):
+        return Expected(self.z, f"g{gi}_")

@@ -508,3 +508,37 @@ def test_cpp_query_files_driver(g1, tmp_path):
             assert head == "q%d" % i
             got = [tuple(int(x) for x in t.split(":")) for t in tops.split(",")] if tops else []
             assert got == want[i], i
+
+
+@pytest.mark.parametrize("gi", range(5))
+def test_other_geometries_match_reference(gi):
+    """databases built and queried by the reference with non-default (k, s, w, stride)
+    (tests/golden/g3.npz): sketches, all-hits and top candidates of the CUDA path"""
+    from metacache_b200.database import Database, SketchingOpt, query_reads
+    from tests.golden_util import G3
+    g3 = G3()
+    k, s, w, stride = g3.geometries[gi]
+    exp = g3.expected(gi)
+    db = Database(0, 1)
+    db.load_part_arrays(0, *g3.part(gi))
+    # the rules of make_candidate_generation_rules use the DATABASE's window stride
+    from metacache_b200 import database as D
+    res = []
+    qb = D.QueryBatch(db, 4096, 1 << 22, 2, True, 1)
+    hd = qb.host_data(0)
+    sk = SketchingOpt(k, s, w, stride)
+    for a, b in g3.reads:
+        rules = D.make_candidate_generation_rules(len(a), len(b), 0, stride, 2)
+        assert qb.add_paired_read(0, a, b, sk, rules)
+    db.query_gpu_async(qb, 0, sk)
+    hd.wait_for_results()
+    for i, (a, b) in enumerate(g3.reads):
+        kept = [x for x, keep in zip(hd.sketches(i), _window_keeps(a, b, k, w, stride)) if keep]
+        assert len(kept) == len(exp.sketches[i]), i
+        for x, y in zip(kept, exp.sketches[i]):
+            assert np.array_equal(x, y), i
+        assert np.array_equal(hd.allhits(i), exp.allhits[i]), i
+        top = [c.as_tuple() for c in hd.top_candidates(i) if c.hits > 0]
+        assert top == exp.top[i], i
+    qb.close()
+    db.close()

@@ -156,3 +156,23 @@ def test_oracle_classification_matches_reference_golden_file():
             assert got == expected[sec][qid], (sec, qid, top)
             classified += t != 0
     assert classified > 150
+
+
+@pytest.mark.parametrize("gi", range(5))
+def test_oracle_matches_reference_for_other_geometries(gi):
+    """(k, s, w, stride) other than the default: databases built and queried by the reference itself
+    (tests/golden/g3.npz) - sketches, sorted all-hits and top candidates"""
+    from tests.golden_util import G3
+    g3 = G3()
+    k, s, w, stride = g3.geometries[gi]
+    exp = g3.expected(gi)
+    tab = O.Table(*g3.part(gi))
+    for i, (a, b) in enumerate(g3.reads):
+        sk = [x for x in O.sketch_sequence(a, k, s, w, stride) if x is not None]
+        sk += [x for x in O.sketch_sequence(b, k, s, w, stride) if x is not None]
+        assert len(sk) == len(exp.sketches[i]), i
+        for x, y in zip(sk, exp.sketches[i]):
+            assert np.array_equal(x, y), i
+        allh, top = O.query(tab, a, b, k, s, w, stride, maxc=2)
+        assert np.array_equal(allh, exp.allhits[i]), i
+        assert top == exp.top[i], i
