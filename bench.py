@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--slot-reads", type=int, default=1_000_000, help="reads per host batch slot (e2e)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicate", action="store_true",
+                    help="N > 1: every GPU holds the SAME single-part database and queries only its own reads "
+                         "(the reference's -replicate mode, SURVEY 8e) instead of the target-sharded database")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default)")
     ap.add_argument("--cache", default=os.environ.get(
@@ -231,20 +234,23 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
-    part = rank if world > 1 else 0
+    sharded = world > 1 and not args.replicate               # else: independent replicas (or one GPU)
+    part = rank if sharded else 0
     threads = os.cpu_count() or 1
 
     if not args.reads:
         args.reads = 10_000_000 if args.workload == "C2" else 2_000_000
-    if args.workload == "C3" and world > 1:
-        raise SystemExit("workload C3 is a single-GPU configuration (BASELINE.json configs[2])")
+    if args.workload == "C3" and sharded:
+        raise SystemExit("workload C3 is a single-GPU configuration (BASELINE.json configs[2]); use --replicate for N > 1")
     db, bases, wins, dbinfo = build_part(args, part, device)
     flat, offs = make_reads(args, bases, rank, device)       # uint8 bases back to back + int64 offsets, on the device
     del bases
     torch.cuda.empty_cache()
     nq = args.reads
     n_bases = int(offs[-1].item())
-    part_desc = "single partition" if world == 1 else f"{world}-way target-partitioned, one part per GPU"
+    part_desc = ("single partition" if world == 1 else
+                 f"{world}-way target-partitioned, one part per GPU" if sharded else
+                 f"single partition replicated on {world} GPUs, every GPU queries its own reads")
     if args.workload == "C2":
         metric = "reads_per_second_150bp"
         workload = (f"C2: {nq} x {READ_LEN}bp synthetic reads (R150) vs {args.targets}-target x "
@@ -257,12 +263,12 @@ def main():
         read_len = round(n_bases / nq, 1)
     config = {"workload": workload, "reads_per_gpu": nq, "read_len": read_len, "targets_per_part": args.targets,
               "db": dbinfo, "l2": "inputs larger than L2 (reads %.1f GB + table %.1f GB per step)" %
-              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": "db-sharded x%d" % world}
+              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": ("db-sharded x%d" if sharded or world == 1 else "replicas x%d") % world}
     per_read_scale = READ_LEN * nq / n_bases                 # CPU samples are sized in 150 bp read equivalents
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
-        if world > 1:
+        if sharded:
             config["reference_db"] = "part 0 only (1/%d of the sharded database)" % world
         base = export_reference_db(args, db, wins, 0)
         sample = args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads) * per_read_scale))
@@ -305,7 +311,7 @@ def main():
     q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), nq, nq, n_bases)
     d_top = torch.empty((nq, MAXC, 4), dtype=torch.int32, device=device)
 
-    if world == 1:
+    if not sharded:
         def step():
             _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), d_top.data_ptr(), sp))
     else:
@@ -326,7 +332,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    nwin_launch = L.mcb200_workspace_num_windows(ws) if world == 1 else 2 * nq
+    nwin_launch = L.mcb200_workspace_num_windows(ws) if not sharded else 2 * nq
     cnt = (C.c_uint64 * 8)()
     _lib.check(L.mcb200_workspace_counters(ws, cnt))         # resets the counters
     _lib.check(L.mcb200_workspace_set_profiling(ws, 1))
@@ -360,7 +366,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     calls = float(args.steps)
-    n_launch = calls * world                                   # fused-kernel launches in the timed region
+    n_launch = calls * (world if sharded else 1)               # fused-kernel launches of this rank in the timed region
     feats_probed, locs, sectors = cnt[4] / n_launch, cnt[3] / n_launch, cnt[5] / n_launch
     list_lines = cnt[6] / n_launch
     alg_bytes = 4 * SK["sketchlen"] * nwin_launch + 16 * feats_probed + 8 * locs + 16 * MAXC * nq + 8 * nq
@@ -371,7 +377,7 @@ def main():
     traffic = None
     try:
         cal = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if world == 1:
+        if not sharded:
             traffic = int(cal["query_fast_kernel"]["dram_bytes_per_read"] * nq)
     except Exception:
         pass
@@ -400,7 +406,7 @@ def main():
 
     # ---------------- e2e: host buffers through the batch API (H2D + kernels + D2H) -----------
     e2e = None
-    if world == 1:
+    if not sharded:
         nslots = (nq + args.slot_reads - 1) // args.slot_reads
         per = args.slot_reads
         host_reads = flat.cpu().numpy()
@@ -442,7 +448,12 @@ def main():
             _lib.check(L.mcb200_batch_span_ms(qb, 0, nslots, C.byref(span)))
             dev_ms.append(span.value)
         e2e_ms = sum(dev_ms) / len(dev_ms)
-        e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
+        if dist is not None:                                     # replicas: the slowest rank sets the step
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+            h2d, d2h = h2d * world, d2h * world
+        e2e = {"value": nq_total / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_ms, 3),
                "wall_ms_per_step": round(sum(wall) / len(wall), 3), "slots": nslots,
                "api": "mcb200_batch_submit/wait over pinned host buffers (query_batch seam)"}
