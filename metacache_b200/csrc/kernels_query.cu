@@ -9,11 +9,14 @@
 // (gpu_hashmap_operations.cuh:847-942, query_batch.cu:542-633,
 // gpu_result_processing.cuh:325-473) is ONE kernel here: a warp owns a read,
 // probes its features, aggregates the returned locations into a small
-// shared-memory hash table keyed by (tgt,win) (a read's hits are dominated by
-// duplicates of a few locations), sorts only the DISTINCT locations and reduces
-// them to the top candidates; only 16 B per candidate go back to HBM.  Reads
-// with too many distinct locations fall through to a CTA-per-read kernel that
-// sorts the raw list (shared memory, or global scratch for huge reads).
+// shared-memory hash table keyed by location (a read's hits are dominated by
+// duplicates of a few locations) and reduces the DISTINCT locations to the top
+// candidates - without sorting when only top hits at rank "sequence" are wanted
+// (query_fast_kernel), with a sort of the distinct locations when the ordered
+// list itself is an output (query_warp_kernel); only 16 B per candidate go back
+// to HBM.  Reads with too many distinct locations fall through to a
+// CTA-per-read kernel that sorts the raw list (shared memory, or global scratch
+// for huge reads).
 //
 // Closed form used for the sliding window (equivalent to the reference's
 // two-pointer scan): with the read's locations sorted ascending as u64 keys
@@ -186,13 +189,19 @@ __device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint
 
 // ---------------------------------------------------------------------------
 // fast path (top hits only, rank "sequence", W <= kMaxLookupW): no sort at all.
-//   1. probe the read's features (one table bucket load per lane)
-//   2. stream the buckets' locations (coalesced, all loads of a wave in flight)
-//      into a per-warp hash table keyed by (tgt,win) that counts multiplicity
-//   3. for every distinct location j: hits(j) = sum of the counts of (tgt, win_j-d),
-//      d = 0..W-1, found by W-1 more lookups in the same table
-//   4. k rounds of warp arg-max on (hits desc, key asc), excluding chosen targets
-// This is the reference's sort + two-pointer scan + stable top-k, reordered.
+//   1. probe the read's features (one 32-byte table sector per lane)
+//   2. fetch the buckets that are not inline sector by sector, consecutive lanes on consecutive
+//      sectors of a bucket (one memory request per 64-byte line), into a dense staging list
+//   3. insert the list, 32 locations per wave, into a per-warp hash table keyed by (tgt, pair of
+//      consecutive windows) with two 16-bit multiplicities; remember the slots that were empty
+//   4. for the one or two windows j of every entry: hits(j) = sum of the counts of (tgt, win_j-d),
+//      d = 0..W-1 = the entry itself + ceil((W-1)/2) lookups of preceding pairs; lanes keep their
+//      best location and their best of another target
+//   5. k rounds of warp arg-max on (hits desc, location asc), excluding chosen targets; the table is
+//      left empty by removing exactly the remembered slots
+// This is the reference's sort + two-pointer scan + stable top-k, reordered.  Reads a pass cannot
+// settle (table too full, W too large) move to the next queue: a second pass with larger tables,
+// then the CTA kernel.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kMaxLookupW = 8;
 constexpr uint32_t kMaxProbe   = 48;
