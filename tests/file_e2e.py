@@ -1,4 +1,7 @@
-"""File in -> top hits out: `query_file` (reader threads + batch slots) on a FASTA file of R150 reads in
+"""Measurement script (not a pytest module; it lives under tests/ because it times the reference CLI from
+oracle/_ref beside our path, which only tests/ and bench.py may do).
+
+File in -> top hits out: `query_file` (reader threads + batch slots) on a FASTA file of R150 reads in
 /dev/shm vs the reference CLI (`metacache query`, all host threads) on the same file and database."""
 import ctypes as C
 import json
@@ -10,7 +13,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from metacache_b200.reader import query_file, SequenceReader  # noqa: E402
