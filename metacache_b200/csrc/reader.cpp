@@ -341,7 +341,10 @@ extern "C" int64_t mcb200_reader_fill_batch (mcb200_reader* r, mcb200_batch* bat
             }
         }
         r->pending = true;
-        if (header_buf && hpos + r->r1.hlen > header_cap) break;               // caller's header buffer is full
+        if (header_buf && hpos + r->r1.hlen > header_cap) {                     // caller's header buffer is full
+            if (added == 0) return mcb200_set_error(MCB200_EINVAL, "header buffer smaller than one header");
+            break;
+        }
         // make_candidate_generation_rules (candidate_structs.hpp:134-151)
         const uint32_t mw = uint32_t(2 + std::max<uint64_t>(r->r1.len + r->r2.len, insert_size_max) / winstride);
         const int rc = mcb200_batch_add_read(batch, slot, r->r1.seq, r->r1.len, r->r2.seq, r->r2.len, mw);
