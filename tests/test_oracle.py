@@ -127,6 +127,7 @@ def test_oracle_classification_matches_reference_golden_file():
     """classify() restatement vs the last column of classified.expected (all three sections)"""
     from metacache_b200 import dbformat, formatting
     from metacache_b200.database import Database
+    from metacache_b200.statistics import ClassificationStatistics
     from oracle import refio
     meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
     c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
@@ -148,14 +149,31 @@ def test_oracle_classification_matches_reference_golden_file():
     runs = {"single": [(s, b"") for _, s in single],
             "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)]}
     classified = 0
+    summaries = {}
     for sec, items in runs.items():
+        cls = []
         for qid, (a, b) in enumerate(items, start=1):
             _, top = O.query(tab, a, b)
             t, r = O.classify(top, lin, hits_min=5)
             got = formatting.format_classification(t, r, meta.taxa)
             assert got == expected[sec][qid], (sec, qid, top)
             classified += t != 0
+            cls.append((t, r))
+        st = ClassificationStatistics()
+        st.assign_batch(np.asarray(cls, np.uint32))
+        summaries[sec] = st.summary_lines()
     assert classified > 150
+    # the per-rank summary block the reference prints after each section (show_taxon_statistics)
+    want, section = {}, None
+    for line in open(os.path.join(C1, "classified.expected")):
+        line = line.rstrip("\n")
+        if line.startswith("# data/"):
+            section = line[7:].split()[0]
+        if line.startswith("# unclassified:") or line.startswith("# classified:") or line.startswith("#   "):
+            want.setdefault(section, []).append(line)
+    for sec in runs:
+        key = next(k for k in want if k.startswith(sec))
+        assert summaries[sec] == want[key], sec
 
 
 @pytest.mark.parametrize("gi", range(5))
