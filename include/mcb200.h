@@ -40,7 +40,8 @@ enum {
     MCB200_ECUDA     = -3,   /* CUDA runtime error (message has the details) */
     MCB200_ENOMEM    = -4,
     MCB200_EIO       = -5,   /* database file could not be read              */
-    MCB200_ESTATE    = -6    /* call order violated                          */
+    MCB200_ESTATE    = -6,   /* call order violated                          */
+    MCB200_EAGAIN    = -7    /* a resource was grown: issue the same call again */
 };
 
 /* hash_dna.hpp:99-163 sketching_options {kmerlen, sketchlen, winlen, winstride}.
@@ -260,6 +261,15 @@ int mcb200_classify_device (mcb200_workspace* ws, const mcb200_candidate* d_top,
                             uint32_t hits_min, float hits_diff_fraction, uint32_t lowest_rank,
                             uint32_t highest_rank, mcb200_classification* d_out, void* stream);
 
+/* The device-resident query calls above are asynchronous.  A read whose location list outgrows
+ * its region of the workspace's global scratch pool (tens of thousands of locations: long reads
+ * against dense buckets) gets EMPTY candidates and raises a sticky flag.  Call this after the
+ * calls of a step (it waits for the stream last used): 0 = every read was processed;
+ * MCB200_EAGAIN = the pool has been grown to fit the largest read seen - issue the query call(s)
+ * again; the flag is cleared.  mcb200_batch_wait and the all-hits path do this themselves.
+ * (The reference sizes its result buffers for the worst case up front, query_batch.cuh:346-354.) */
+int mcb200_workspace_check (mcb200_workspace* ws);
+
 /* workspace introspection (device pointers, valid after the calls above)     */
 uint32_t        mcb200_workspace_num_windows   (const mcb200_workspace* ws);   /* syncs */
 const uint32_t* mcb200_workspace_sketches      (const mcb200_workspace* ws);   /* [nwin][sketchlen] */
@@ -296,7 +306,8 @@ mcb200_reader* mcb200_reader_open  (const char* filename1, const char* filename2
 /* unpaired reader over the records that START in [byte_begin, byte_end) of an
  * uncompressed file: disjoint ranges give disjoint record sets, so one reader
  * per host thread replaces the reference's single reader thread
- * (database_query.hpp:257-281).  FASTQ ranges assume one sequence line per record. */
+ * (database_query.hpp:257-281).  FASTQ records may have multi-line sequences (one quality line, as
+ * the reference's grammar has it).                                                              */
 mcb200_reader* mcb200_reader_open_range (const char* filename, uint64_t byte_begin, uint64_t byte_end);
 void     mcb200_reader_close (mcb200_reader* r);
 uint64_t mcb200_reader_index (const mcb200_reader* r);      /* queries delivered so far */

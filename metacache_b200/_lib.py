@@ -16,6 +16,9 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "mcb200.h")
 CSRC = os.path.join(HERE, "csrc")
 
 
+EAGAIN = -7          # MCB200_EAGAIN: a resource was grown, issue the same call again
+
+
 class Mcb200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libmcb200 error {code}: {msg}")
@@ -127,6 +130,7 @@ _SIGS = {
     "mcb200_workspace_allhits": (_P, [_P]),
     "mcb200_workspace_allhits_offsets": (_P, [_P]),
     "mcb200_workspace_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "mcb200_workspace_check": (C.c_int, [_P]),
     "mcb200_workspace_set_profiling": (C.c_int, [_P, C.c_int]),
     "mcb200_workspace_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mcb200_workspace_set_warp_capacity": (C.c_int, [_P, C.c_uint32]),

@@ -12,7 +12,7 @@
 #include <vector>
 
 namespace mcb {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 using namespace mcb;
 
@@ -40,7 +40,7 @@ extern "C" int mcb200_device_count (void) {
     return n;
 }
 extern "C" uint32_t mcb200_max_supported_locations_per_feature (void) { return 254; }
-extern "C" uint64_t mcb200_kernel_launches (void) { return g_launches; }
+extern "C" uint64_t mcb200_kernel_launches (void) { return g_launches.load(std::memory_order_relaxed); }
 
 // grow-only device buffer
 template <class T> struct DevBuf {
@@ -112,20 +112,22 @@ static int use_device (int device) {
     return 0;
 }
 
+extern "C" void mcb200_db_close (mcb200_db* db);
+
 extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
     if (n_parts == 0) { fail(MCB200_EINVAL, "n_parts must be >= 1"); return nullptr; }
     if (use_device(device) != 0) return nullptr;
+    cudaDeviceProp prop;
+    CUP(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        fail(MCB200_ENODEVICE, "device %d is sm_%d%d; libmcb200 is built for sm_100a only", device, prop.major, prop.minor);
+        return nullptr;
+    }
     mcb200_db* db = new (std::nothrow) mcb200_db;
     if (!db) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
     db->device = device;
     db->parts.resize(n_parts);
-    cudaDeviceProp prop;
-    CUP(cudaGetDeviceProperties(&prop, device));
     db->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) {
-        fail(MCB200_ENODEVICE, "device %d is sm_%d%d; libmcb200 is built for sm_100a only", device, prop.major, prop.minor);
-        delete db; return nullptr;
-    }
     // random 32-byte bucket probes: ask L2 not to over-fetch neighbouring sectors from HBM
     {
         size_t gran = 32;
@@ -134,9 +136,14 @@ extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
             if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
         }
     }
-    CUP(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
-    CUP(cudaMalloc(&db->d_error, sizeof(int)));
-    CUP(cudaMemset(db->d_error, 0, sizeof(int)));
+    cudaError_t e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_error, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(db->d_error, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        fail(MCB200_ECUDA, "opening the store on device %d failed: %s", device, cudaGetErrorString(e));
+        mcb200_db_close(db);           // releases whatever was created
+        return nullptr;
+    }
     return db;
 }
 
@@ -529,6 +536,39 @@ static int ensure_scratch (mcb200_workspace* ws, uint64_t entries) {
     return 0;
 }
 
+// default pool: one region of 32 Ki entries per CTA of the global-memory tier (kernels_query.cu)
+static int ensure_default_scratch (mcb200_workspace* ws) {
+    if (ws->scratch_entries) return 0;
+    return ensure_scratch(ws, uint64_t(ws->db->sm_count) * 32768ull);
+}
+
+// Reads (and clears) the sticky device flag of the workspace after `st` has drained.  Flag 3 = a read
+// outgrew its region of the scratch pool and got empty candidates: the pool is grown so that the
+// largest read seen fits and MCB200_EAGAIN tells the caller to issue the query call again.
+static int check_overflow (mcb200_workspace* ws, cudaStream_t st) {
+    int err = 0;
+    unsigned long long need = 0;
+    CU(cudaMemcpyAsync(&err, ws->error.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&need, ws->scratch_cursor.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (err == 0) return 0;
+    CU(cudaMemsetAsync(ws->error.p, 0, sizeof(int), st));
+    CU(cudaStreamSynchronize(st));
+    if (err != 3) return fail(MCB200_ECUDA, "device error flag %d", err);
+    uint64_t want = std::max<uint64_t>(ws->scratch_entries * 4, uint64_t(need) * uint64_t(ws->db->sm_count));
+    if (want * 12 > (64ull << 30)) return fail(MCB200_ENOMEM, "scratch pool exhausted: a read needs %llu list entries", need);
+    int rc = ensure_scratch(ws, want);
+    if (rc) return rc;
+    return fail(MCB200_EAGAIN, "scratch pool grown to %llu entries for a read with %llu locations: issue the query call again",
+                (unsigned long long)want, need);
+}
+
+extern "C" int mcb200_workspace_check (mcb200_workspace* ws) {
+    if (!ws) return fail(MCB200_EINVAL, "null argument");
+    CU(cudaSetDevice(ws->db->device));
+    return check_overflow(ws, ws->last_stream);
+}
+
 static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top) {
     const Part& p = ws->db->parts[part];
     QueryArgs a{};
@@ -547,7 +587,7 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
 
 static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
                        const uint64_t* allhits_off, cudaStream_t st) {
-    if (ws->scratch_entries == 0) { int rc = ensure_scratch(ws, 1ull << 22); if (rc) return rc; }
+    { int rc = ensure_default_scratch(ws); if (rc) return rc; }
     QueryArgs a = make_args(ws, part, d_top);
     if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
     CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
@@ -573,8 +613,8 @@ extern "C" int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mc
     if (ws->q.n_queries == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ws->last_stream = st;
-    // a read that outgrows the scratch pool raises the sticky device flag 3; callers see it
-    // through mcb200_workspace_counters() (device API) or batch_wait (which grows and retries)
+    // asynchronous: a read that outgrows the scratch pool raises the sticky device flag 3 and gets
+    // empty candidates; mcb200_workspace_check() reports it (and grows the pool) after the stream drained
     return query_part(ws, part, d_top, nullptr, st);
 }
 
@@ -591,7 +631,7 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
     if (n_queries == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ws->last_stream = st;
-    if (ws->scratch_entries == 0) { int rc = ensure_scratch(ws, 1ull << 22); if (rc) return rc; }
+    { int rc = ensure_default_scratch(ws); if (rc) return rc; }
     mcb200_dev_queries q{}; q.max_win = d_max_win; q.n_queries = n_queries;
     const mcb200_dev_queries saved_q = ws->q; const SketchParams saved_sk = ws->sk;
     ws->q = q; ws->sk.s = sketchlen;
@@ -691,16 +731,12 @@ extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queri
             if (ws->profiling && ws->ev) { CU(cudaEventRecord(ws->ev->merge[1], st)); ws->ev->merged = true; }
             CU(cudaGetLastError());
         }
-        // The scratch-pool check needs a sync; callers on the fast path check it
-        // later through mcb200_workspace_counters()/batch_wait (sticky flag).
+        // The scratch-pool check needs a sync: the asynchronous top-hits path leaves it to the caller
+        // (mcb200_workspace_check after its own synchronisation, or mcb200_batch_wait); the all-hits
+        // path has synchronised already, so it checks and re-issues here.
         if (!ws->want_allhits) return 0;
-        int err = 0;
-        CU(cudaMemcpyAsync(&err, ws->error.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (err != 3) return 0;
-        CU(cudaMemsetAsync(ws->error.p, 0, sizeof(int), st));
-        rc = ensure_scratch(ws, ws->scratch_entries * 8);
-        if (rc) return rc;
+        rc = check_overflow(ws, st);
+        if (rc != MCB200_EAGAIN) return rc;
     }
     return fail(MCB200_ENOMEM, "scratch pool exhausted");
 }
@@ -749,8 +785,7 @@ extern "C" int mcb200_workspace_counters (mcb200_workspace* ws, uint64_t out[8])
     CU(cudaStreamSynchronize(ws->last_stream));
     for (int i = 0; i < 8; ++i) out[i] = 0;
     for (int s = 0; s < 64; ++s) for (int i = 0; i < 8; ++i) out[i] += h[s * 8 + i];
-    if (err == 3) return fail(MCB200_ENOMEM, "scratch pool exhausted by a huge read; results of that read are empty");
-    if (err) return fail(MCB200_ECUDA, "device error flag %d", err);
+    if (err) return check_overflow(ws, ws->last_stream);     // clears the flag, grows the pool, MCB200_EAGAIN
     return 0;
 }
 
@@ -821,20 +856,24 @@ extern "C" int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
         const uint64_t nb = h_off[t1] - h_off[t0];
         if (nb >= (1ull << 32) - 8192) return fail(MCB200_EINVAL, "target %u too long for the device builder", t0);
         const uint32_t ns = t1 - t0;
-        if ((h_off[t0] & 15) != 0) {
-            // bulk/vector loads need 16-byte alignment: copy the chunk to an aligned buffer
-        }
         mcb200_workspace* ws = mcb200_workspace_create(db, ns, ns, nb + 16, 1, 0);
-        if (!ws) return MCB200_ECUDA;
+        if (!ws) return MCB200_ECUDA;          // last_error set by workspace_create
         DevBuf<char> aligned;
         const char* bases = d_bases + h_off[t0];
+        cudaError_t ce = cudaSuccess;
         if (reinterpret_cast<uintptr_t>(bases) & 15) {
-            cudaError_t e = aligned.ensure(nb + 64);
-            if (e != cudaSuccess) { mcb200_workspace_destroy(ws); return fail(MCB200_ECUDA, "alloc failed"); }
-            cudaMemcpyAsync(aligned.p, bases, nb, cudaMemcpyDeviceToDevice, st);
+            // bulk/vector loads need 16-byte alignment: copy the chunk to an aligned buffer
+            ce = aligned.ensure(nb + 64);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(aligned.p, bases, nb, cudaMemcpyDeviceToDevice, st);
             bases = aligned.p;
         }
-        seq_off32.ensure(ns + 1); seq_query.ensure(ns); dummy_maxwin.ensure(ns);
+        if (ce == cudaSuccess) ce = seq_off32.ensure(ns + 1);
+        if (ce == cudaSuccess) ce = seq_query.ensure(ns);
+        if (ce == cudaSuccess) ce = dummy_maxwin.ensure(ns);
+        if (ce != cudaSuccess) {
+            mcb200_workspace_destroy(ws); aligned.release();
+            return fail(MCB200_ECUDA, "device part build: allocation failed: %s", cudaGetErrorString(ce));
+        }
         offsets64_to_32_kernel<<<(ns + 1 + 255) / 256, 256, 0, st>>>(d_seq_offsets + t0, seq_off32.p, h_off[t0], ns + 1);
         iota_kernel<<<(ns + 255) / 256, 256, 0, st>>>(seq_query.p, ns);
         count_launch(2);
@@ -843,14 +882,16 @@ extern "C" int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
         if (rc) { mcb200_workspace_destroy(ws); aligned.release(); return rc; }
         const uint32_t nw = mcb200_workspace_num_windows(ws);
         std::vector<uint32_t> hw(ns + 1);
-        cudaMemcpyAsync(hw.data(), ws->seq_win_off.p, (ns + 1) * 4, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(feats.p + win_done * sp.s, ws->feats.p, uint64_t(nw) * sp.s * 4, cudaMemcpyDeviceToDevice, st);
-        if (out_windows) {
+        cudaError_t e = cudaMemcpyAsync(hw.data(), ws->seq_win_off.p, (ns + 1) * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && win_done + nw > total_windows) e = cudaErrorInvalidValue;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(feats.p + win_done * sp.s, ws->feats.p, uint64_t(nw) * sp.s * 4, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && out_windows) {
             consumed_windows_kernel<<<(ns + 255) / 256, 256, 0, st>>>(seq_off32.p, ns, sp, ws->seq_nwin.p);
             count_launch();
-            cudaMemcpyAsync(out_windows + t0, ws->seq_nwin.p, ns * 4, cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(out_windows + t0, ws->seq_nwin.p, ns * 4, cudaMemcpyDeviceToHost, st);
         }
-        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         mcb200_workspace_destroy(ws); aligned.release();
         if (e != cudaSuccess) return fail(MCB200_ECUDA, "target sketching failed: %s", cudaGetErrorString(e));
         for (uint32_t i = 0; i <= ns; ++i) h_seq_win_off[t0 + i] = uint32_t(win_done + hw[i]);
@@ -1070,20 +1111,16 @@ extern "C" int mcb200_batch_wait (mcb200_batch* b, uint32_t slot) {
         cudaEventElapsedTime(&s.kernels_ms, s.ev_k0, s.ev_k1);
         s.waited = true;
         if (s.n_queries) {
-            int err = 0;
-            CU(cudaMemcpy(&err, s.ws->error.p, sizeof(int), cudaMemcpyDeviceToHost));
-            if (err == 3) {
-                // a huge read outgrew the scratch pool: grow and redo this submit
-                CU(cudaMemset(s.ws->error.p, 0, sizeof(int)));
-                int rc = ensure_scratch(s.ws, s.ws->scratch_entries * 8);
-                if (rc) return rc;
+            int rc = check_overflow(s.ws, s.stream);
+            if (rc == MCB200_EAGAIN) {
+                // a huge read outgrew its scratch region (pool grown by the check): redo this submit
                 const mcb200_sketching sk{s.ws->sk.k, s.ws->sk.s, s.ws->sk.w, s.ws->sk.stride};
                 s.waited = false;
                 rc = mcb200_batch_submit(b, slot, &sk);
                 if (rc) return rc;
                 return mcb200_batch_wait(b, slot);
             }
-            if (err) return fail(MCB200_ECUDA, "device error flag %d", err);
+            if (rc) return rc;
         }
     }
     return 0;

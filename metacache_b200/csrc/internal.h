@@ -1,5 +1,6 @@
 // Host-side declarations of the kernel launchers (one per .cu file).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/mcb200.h"
@@ -7,8 +8,17 @@
 
 namespace mcb {
 
-extern unsigned long long g_launches;   // kernels launched by this library (api.cu)
-inline void count_launch (unsigned n = 1) { g_launches += n; }
+extern std::atomic<unsigned long long> g_launches;   // kernels launched by this library (api.cu)
+inline void count_launch (unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Function attributes (MaxDynamicSharedMemorySize) are per DEVICE: returns true the first time it
+// is called with `mask` on the current device, from whatever host thread (one bit per device id).
+inline bool first_use_on_device (std::atomic<uint64_t>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (unsigned(dev) & 63u);
+    return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 
 struct SketchParams { uint32_t k, s, w, stride; };
 

@@ -733,13 +733,12 @@ query_warp_kernel (QueryArgs a, uint32_t T)
 void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st)
 {
     if (!a.nq) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devices{0};
+    if (first_use_on_device(attr_devices)) {
         cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
     }
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
     if (!a.tax_of_tgt && !a.allhits) {
@@ -820,7 +819,6 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
     __shared__ uint32_t s_chosen[kMaxCand];
     __shared__ uint32_t s_red_c[kHeavyThreads / 32], s_red_j[kHeavyThreads / 32];
     __shared__ uint32_t s_q, s_bc;
-    __shared__ unsigned long long s_goff;
     __shared__ unsigned long long s_cnt[4];
 
     uint64_t* sh_keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -863,13 +861,18 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
             if (tid == 0) a.heavy_list[size_t(in_queue + 1) * nq_cap + atomicAdd(a.heavy_count + 2 * (in_queue + 1), 1u)] = q;
             continue;
         } else {
-            if (tid == 0) s_goff = atomicAdd(a.scratch_cursor, (unsigned long long)n);
-            __syncthreads();
-            const unsigned long long off = s_goff;
-            if (off + n > a.scratch_entries) {            // host grows the pool and retries
-                if (tid == 0) { atomicExch(a.error, 3); write_empty(top, 0, a.maxc); }
+            // every CTA of this tier owns one region of the global scratch pool and reuses it for
+            // each of its reads, so only a single read larger than a region can fail: flag 3 tells
+            // the host to grow the pool (to at least the size left in scratch_cursor) and re-issue
+            const unsigned long long region = a.scratch_entries / gridDim.x;
+            if (n > region) {
+                if (tid == 0) {
+                    atomicMax(a.scratch_cursor, (unsigned long long)n);
+                    atomicExch(a.error, 3); write_empty(top, 0, a.maxc);
+                }
                 continue;
             }
+            const unsigned long long off = region * blockIdx.x;
             keys = a.scratch + off;
             cnt  = reinterpret_cast<uint32_t*>(a.scratch + a.scratch_entries) + off;
         }
@@ -979,12 +982,10 @@ constexpr int      kHeavyBig   = 1024;           // tier 1: the one CTA of an SM
 
 void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
 {
-    static bool attr_set = false;
+    static std::atomic<uint64_t> attr_devices{0};
     const size_t smem = size_t(kHeavySmemEntries) * 12;
-    if (!attr_set) {
+    if (first_use_on_device(attr_devices))
         cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr_set = true;
-    }
     // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
     const uint32_t in_queue = (!a.tax_of_tgt && !a.allhits) ? 1u : 0u;
     query_heavy_kernel<kHeavySmall><<<sm_count * 8, kHeavySmall, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);

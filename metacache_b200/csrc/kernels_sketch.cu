@@ -541,11 +541,10 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
                     const uint32_t* seq_win_off, const uint32_t* win_seq, const uint32_t* d_nwin,
                     SketchParams p, uint32_t* feats, int sm_count, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devices{0};
+    if (first_use_on_device(attr_devices)) {
         cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(sketch_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
     }
     static const int ctas_per_sm = [] { const char* e = getenv("MCB200_SKETCH_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
     static const bool no_fast = getenv("MCB200_SKETCH_WARP") != nullptr;     // testing aid: warp-per-window kernel only

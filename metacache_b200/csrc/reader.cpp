@@ -14,6 +14,7 @@
 #include "../../include/mcb200.h"
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -43,6 +44,7 @@ struct Input {
     uint64_t buf_pos = 0;          // file offset of buf[0] (plain files)
     uint64_t limit = ~0ull;        // records starting at or after this file offset are not ours
     std::string scratch;           // multi-line sequences are joined here
+    std::string io_error;          // set by refill() when the source failed (eof stays false)
 
     bool open (const char* path, std::string& err) {
         const int f = ::open(path, O_RDONLY);
@@ -81,7 +83,22 @@ struct Input {
         long got;
         if (gz) got = gzread(gz, buf.data() + end, unsigned(std::min<size_t>(want, 1u << 30)));
         else    got = long(::read(fd, buf.data() + end, want));
-        if (got <= 0) { eof = true; return false; }
+        if (got < 0) {                                            // I/O error: NOT an end of input
+            io_error = gz ? "error while decompressing the input" : (std::string("read failed: ") + strerror(errno));
+            return false;
+        }
+        if (got == 0) {
+            if (gz) {                                             // a truncated / corrupt stream ends with an error state
+                int zerr = Z_OK;
+                const char* msg = gzerror(gz, &zerr);
+                if (zerr != Z_OK && zerr != Z_STREAM_END) {
+                    io_error = std::string("corrupt or truncated gzip input: ") + (msg ? msg : "");
+                    return false;
+                }
+            }
+            eof = true;
+            return false;
+        }
         end += size_t(got);
         return true;
     }
@@ -159,7 +176,7 @@ struct Source {
                 return true;
             }
             if (used < 0) return false;
-            if (!in.refill() && !in.eof) { err = "read error"; return false; }
+            if (!in.refill() && !in.eof) { err = in.io_error.empty() ? std::string("read error") : in.io_error; return false; }
         }
     }
 };
@@ -207,14 +224,22 @@ extern "C" mcb200_reader* mcb200_reader_open (const char* filename1, const char*
 }
 
 // First record that starts at or after file offset `pos` of an uncompressed file.  FASTA: a line
-// starting with '>'.  FASTQ: a line starting with '@' whose third line starts with '+' and whose
-// second and fourth lines have the same length (a quality line may start with '@' too).
+// starting with '>'.  FASTQ: a line starting with '@' is a header or a quality line (sequence and
+// '+' lines never start with '@'); the grammar has exactly ONE quality line per record
+// (sequence_io.cpp:203-223) and it is followed by the next header, while a header is followed by a
+// sequence or '+' line.  So "'@' line followed by another '@' line" = quality line, the record
+// starts at the second one; any other '@' line is a header.  Multi-line sequences are fine.
 static bool sync_to_record (Input& in, uint64_t pos, bool fastq, std::string& err) {
     if (pos == 0) return in.seek(0);
     if (!in.seek(pos - 1)) { err = "seek failed"; return false; }
     size_t scan = 0;                       // buffer offset the search for the next line break starts at
+    auto more = [&] () -> bool {           // false: nothing further (end of file, or an I/O error left in `err`)
+        if (in.refill()) return true;
+        if (!in.eof) err = in.io_error.empty() ? std::string("read error") : in.io_error;
+        return false;
+    };
     for (;;) {                             // (data stays at buf[0]: beg == 0 throughout)
-        if (in.end == scan) { in.refill(); if (in.end == scan) { in.beg = in.end; return true; } }
+        if (in.end == scan && !more()) { in.beg = in.end; return err.empty(); }
         const char* base = in.buf.data();
         const char* e = base + in.end;
         const char* nl = find_nl(base + scan, e);
@@ -224,26 +249,25 @@ static bool sync_to_record (Input& in, uint64_t pos, bool fastq, std::string& er
             continue;
         }
         const size_t l0 = size_t(nl + 1 - base);
-        if (l0 >= in.end) {
-            if (in.eof) { in.beg = in.end; return true; }
-            in.refill();
-            if (in.end <= l0 && in.eof) { in.beg = in.end; return true; }
+        if (l0 >= in.end) {                // the line break is the last byte we have
+            if (!more()) { in.beg = in.end; return err.empty(); }
             continue;                      // same line break again, now with data behind it
         }
-        bool accept = false;
-        if (!fastq) accept = (base[l0] == '>');
-        else if (base[l0] == '@') {
+        if (!fastq) {
+            if (base[l0] == '>') { in.beg = l0; return true; }
+        } else if (base[l0] == '@') {
             const char* n0 = find_nl(base + l0, e);
-            const char* n1 = n0 ? find_nl(n0 + 1, e) : nullptr;
-            const char* n2 = n1 ? find_nl(n1 + 1, e) : nullptr;
-            const char* n3 = n2 ? find_nl(n2 + 1, e) : nullptr;
-            if (!n3 && !in.eof) { in.refill(); continue; }          // need the whole candidate record
-            if (n2) {
-                const char* q_end = n3 ? n3 : e;
-                accept = (n1[1] == '+') && ((n1 - n0) == (q_end - n2));
-            } else accept = (n1 != nullptr && n1 + 1 < e && n1[1] == '+');   // truncated last record
+            if (!n0 || n0 + 1 >= e) {      // need the first character of the following line
+                if (more()) continue;
+                if (!err.empty()) return false;
+                // '@' line that is the last line of the file: in a well-formed file that is the quality
+                // line of the record before (a header is always followed by at least one more line)
+                in.beg = in.end;
+                return true;
+            }
+            in.beg = (n0[1] == '@') ? size_t(n0 + 1 - base) : l0;
+            return true;
         }
-        if (accept) { in.beg = l0; return true; }
         scan = l0;
     }
 }

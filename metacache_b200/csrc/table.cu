@@ -160,22 +160,26 @@ int table_export (const Bucket* buckets, uint64_t nbuckets, const void* values, 
     uint64_t *sz64 = nullptr, *vpos = nullptr, *ovals = nullptr;
     uint8_t* osizes = nullptr;
     void* tmp = nullptr; size_t tmpb = 0;
-    cudaMalloc(&occ, nslots * 4); cudaMalloc(&sz, nslots * 4); cudaMalloc(&kpos, nslots * 4);
-    cudaMalloc(&sz64, nslots * 8); cudaMalloc(&vpos, nslots * 8);
-    cudaMalloc(&okeys, nkeys * 4); cudaMalloc(&osizes, nkeys);
-    cudaMalloc(&ovals, (nvalues ? nvalues : 1) * 8);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&] (cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
     const unsigned grid = unsigned((nslots + 255) / 256);
-    slot_sizes_kernel<<<grid, 256, 0, st>>>(buckets, nslots, occ, sz);
-    widen_kernel<<<grid, 256, 0, st>>>(sz, sz64, nslots);
-    count_launch(2);
-    device_scan_u32(occ, kpos, nslots, tmp, tmpb, st);
-    device_scan_u64(sz64, vpos, nslots, tmp, tmpb, st);
-    slot_export_kernel<<<grid, 256, 0, st>>>(buckets, nslots, view, kpos, vpos, okeys, osizes, ovals);
-    count_launch();
-    cudaMemcpyAsync(h_keys, okeys, nkeys * 4, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(h_sizes, osizes, nkeys, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(h_values, ovals, nvalues * 8, cudaMemcpyDeviceToHost, st);
-    const cudaError_t e = cudaStreamSynchronize(st);
+    if (ok(cudaMalloc(&occ, nslots * 4)) && ok(cudaMalloc(&sz, nslots * 4)) && ok(cudaMalloc(&kpos, nslots * 4)) &&
+        ok(cudaMalloc(&sz64, nslots * 8)) && ok(cudaMalloc(&vpos, nslots * 8)) &&
+        ok(cudaMalloc(&okeys, nkeys * 4)) && ok(cudaMalloc(&osizes, nkeys)) &&
+        ok(cudaMalloc(&ovals, (nvalues ? nvalues : 1) * 8))) {
+        slot_sizes_kernel<<<grid, 256, 0, st>>>(buckets, nslots, occ, sz);
+        widen_kernel<<<grid, 256, 0, st>>>(sz, sz64, nslots);
+        count_launch(2);
+        device_scan_u32(occ, kpos, nslots, tmp, tmpb, st);
+        device_scan_u64(sz64, vpos, nslots, tmp, tmpb, st);
+        slot_export_kernel<<<grid, 256, 0, st>>>(buckets, nslots, view, kpos, vpos, okeys, osizes, ovals);
+        count_launch();
+        ok(cudaGetLastError());
+        ok(cudaMemcpyAsync(h_keys, okeys, nkeys * 4, cudaMemcpyDeviceToHost, st));
+        ok(cudaMemcpyAsync(h_sizes, osizes, nkeys, cudaMemcpyDeviceToHost, st));
+        ok(cudaMemcpyAsync(h_values, ovals, nvalues * 8, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+    }
     cudaFree(occ); cudaFree(sz); cudaFree(kpos); cudaFree(sz64); cudaFree(vpos);
     cudaFree(okeys); cudaFree(osizes); cudaFree(ovals); if (tmp) cudaFree(tmp);
     return e == cudaSuccess ? 0 : -1;

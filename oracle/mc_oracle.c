@@ -6,7 +6,7 @@
  * cpu_baseline / --impl reference legs may load this; the product path
  * (metacache_b200/) never does.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file
+ * Parity status: PINNED.  tests/test_oracle.py checks this file
  * against (1) the known-answer vectors generated from the reference headers
  * (SURVEY.md 4.3), (2) fixtures produced by the reference itself
  * (oracle/ref_harness.cpp linking the unmodified reference objects; committed

@@ -146,3 +146,64 @@ def test_cpp_reader_skip(tmp_path):
     for k in (0, 1, 7, 19999, 20000, 30000):
         part = _parse_dump(subprocess.run([_dump_exe(), path, "", str(k)], capture_output=True).stdout)["records"]
         assert part == whole[k:]
+
+
+def _multiline_fastq(n, seed):
+    """FASTQ with multi-line sequences and ONE quality line per record (the grammar the reference
+    reader accepts, sequence_io.cpp:203-223); quality lines start with '@' every few records."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        ln = int(rng.integers(0, 400))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), ln))
+        width = int(rng.integers(20, 90))
+        lines = [seq[j:j + width] for j in range(0, ln, width)] or [b""]
+        if i % 11 == 3:
+            lines = lines[:1] + [b""] + lines[1:]                      # an empty line inside the sequence
+        qual = bytes(rng.integers(33, 74, ln, dtype=np.uint8))
+        if i % 3 == 0 and ln:
+            qual = b"@" + qual[1:]
+        out.append(b"@r%d some text\n" % i + b"\n".join(lines) + b"\n+" + (b"r%d" % i if i % 2 else b"") + b"\n" + qual + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("nranges", [2, 4, 7, 33])
+def test_byte_ranges_on_multiline_fastq(nranges, tmp_path):
+    """range readers must resynchronise on FASTQ records with multi-line sequences too"""
+    path = os.path.join(str(tmp_path), "ml.fq")
+    open(path, "wb").write(_multiline_fastq(400, 5))
+    with SequenceReader(path) as r:
+        whole = [(h, a) for h, a, _ in r]
+    assert len(whole) == 400
+    size = os.path.getsize(path)
+    rng = np.random.default_rng(100 + nranges)
+    cuts = sorted(set([0, size] + [int(x) for x in rng.integers(0, size + 1, nranges - 1)]))
+    got = []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        with SequenceReader(path, byte_range=(b, e)) as r:
+            got += [(h, a) for h, a, _ in r]
+    assert got == whole
+    # every possible cut position of a small file
+    small = os.path.join(str(tmp_path), "ml_small.fq")
+    open(small, "wb").write(_multiline_fastq(6, 9))
+    with SequenceReader(small) as r:
+        whole = [(h, a) for h, a, _ in r]
+    size = os.path.getsize(small)
+    for cut in range(0, size + 1):
+        got = []
+        for b, e in ((0, cut), (cut, size)):
+            with SequenceReader(small, byte_range=(b, e)) as r:
+                got += [(h, a) for h, a, _ in r]
+        assert got == whole, cut
+
+
+def test_truncated_gzip_is_an_error_not_an_end_of_input(tmp_path):
+    """a corrupt / truncated gzip stream must not look like a clean end of the reads"""
+    raw = b"".join(b">r%d\n%s\n" % (i, b"ACGT" * 40) for i in range(20000))
+    z = gzip.compress(raw)
+    path = os.path.join(str(tmp_path), "trunc.fa.gz")
+    open(path, "wb").write(z[:len(z) // 2])
+    with pytest.raises(Mcb200Error):
+        with SequenceReader(path) as r:
+            n = sum(1 for _ in r)
+            raise AssertionError(f"read {n} records from a truncated gzip file without an error")
