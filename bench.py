@@ -183,16 +183,33 @@ def write_reads_txt(path, flat_np, offs_np):
     out.tofile(path)
 
 
-def cpu_reference_run(base, flat_np, offs_np, threads, passes):
+def cpu_reference_run(base, flat_np, offs_np, threads, passes, tops=None):
     """the reference's own hot path (oracle/_ref/mc_ref_harness links the unmodified reference
-    objects) on `threads` host threads; returns dict with per-pass seconds"""
+    objects) on `threads` host threads; returns dict with per-pass seconds.  tops: file that
+    receives the reference's top candidates of every read ([n][MAXC][4] u32) for the parity check"""
     from oracle import refio
     if not os.path.exists(refio.HARNESS):
         return None
     rt = base + f".reads{len(offs_np) - 1}_{int(offs_np[-1] - offs_np[0])}.txt"
     if not os.path.exists(rt):
         write_reads_txt(rt, flat_np, offs_np)
-    return refio.run_harness(base, rt, "-", threads=threads, repeat=passes, sketches=0, allhits=0)
+    kw = dict(threads=threads, repeat=passes, sketches=0, allhits=0, maxcand=MAXC)
+    if tops:
+        kw["tops"] = tops
+    return refio.run_harness(base, rt, "-", **kw)
+
+
+def parity_against_reference(tops_file, gpu_top):
+    """bit-exact comparison of the reference's top candidates (harness dump) with the rows the GPU
+    produced for the same reads: {tgt, hits, beg, end} x MAXC, unused entries {~0, 0, 0, 0}"""
+    ref = np.fromfile(tops_file, dtype="<u4").reshape(-1, MAXC, 4)
+    got = np.ascontiguousarray(gpu_top[:len(ref)]).view(np.uint32).reshape(-1, MAXC, 4)
+    bad = np.flatnonzero((ref != got).any(axis=(1, 2)))
+    out = {"reads": int(len(ref)), "mismatches": int(len(bad)), "reads_with_hits": int((ref[:, 0, 1] > 0).sum()),
+           "against": "reference database::query_host top candidates (oracle/_ref/mc_ref_harness), same database file, same reads"}
+    if len(bad):
+        out["first_mismatch"] = {"read": int(bad[0]), "reference": ref[bad[0]].tolist(), "gpu": got[bad[0]].tolist()}
+    return out
 
 
 def cpu_port_run(db, flat_np, offs_np):
@@ -316,7 +333,7 @@ def main():
             _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), d_top.data_ptr(), sp))
     else:
         from metacache_b200.distributed import ShardedQuery
-        nwin = sum(1 for _ in range(2)) * nq     # 150 bp reads: two windows each
+        nwin = 2 * nq                            # 150 bp reads: two windows each
         sq = ShardedQuery(db, ws, nq, nwin, SK["sketchlen"], MAXC, device, stream)
         d_top = sq.top
 
@@ -352,6 +369,10 @@ def main():
     _lib.check(L.mcb200_workspace_stage_times(ws, stage))
     _lib.check(L.mcb200_workspace_set_profiling(ws, 0))
     _lib.check(L.mcb200_workspace_counters(ws, cnt))
+    _lib.check(L.mcb200_workspace_check(ws))                 # no read may have been dropped (scratch overflow)
+    # rows of the first reads, kept for the bit-exact comparison with the reference below
+    keep = int(min(nq, max(200_000, 100_000 * threads) * per_read_scale)) if not args.cpu_sample else args.cpu_sample
+    top_first = d_top[:keep].cpu().numpy() if not sharded else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -490,14 +511,18 @@ def main():
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
+    parity = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
             base = export_reference_db(args, db, wins, 0)
             sample = args.cpu_sample or int(min(nq, max(200_000, 100_000 * threads) * per_read_scale))
             offs_np = host_offs[:sample + 1].astype(np.int64)
             flat_np = host_reads[:int(offs_np[-1])]
-            r = cpu_reference_run(base, flat_np, offs_np, threads, 2)
+            tops_file = base + f".tops{sample}.bin"
+            r = cpu_reference_run(base, flat_np, offs_np, threads, 2, tops=tops_file)
             if r is not None:
+                parity = parity_against_reference(tops_file, top_first[:sample])
+                os.unlink(tops_file)
                 cpu = {"value": sample / r["passes"][-1], "unit": "reads/s", "cores": threads, "kind": "reference",
                        "sample": f"first {sample} reads of the workload, reference hot path (database::query_host) "
                                  f"via oracle/_ref/mc_ref_harness, {threads} threads, 2nd of 2 passes; "
@@ -515,7 +540,7 @@ def main():
         out = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64", "data": "synthetic", "config": config,
-               "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+               "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()

@@ -19,7 +19,11 @@
  *   reads.txt : one query per line, "SEQ1" or "SEQ1 SEQ2" (paired); the token
  *               "-" stands for an empty sequence
  *   keys      : maxcand=2 insert=0 part=-1 threads=1 repeat=1 sketches=1
- *               allhits=1
+ *               allhits=1 tops=<file> first=0 count=all
+ *   tops=<file>: fixed-size dump of the top candidates only (for parity checks at benchmark scale):
+ *               u32 LE [nreads][maxcand][4] = {tgt,hits,beg,end}, unused entries {~0,0,0,0} -
+ *               the layout of the library's mcb200_candidate rows.  first/count select a slice of
+ *               the reads file.
  * output (all u32 LE):
  *   magic 0x4d435246 ("MCRF"), nreads
  *   per read: nsk, {len, feat[len]} x nsk, nall, {win,tgt} x nall,
@@ -62,6 +66,13 @@ sequence to_seq (const std::string& s, size_t b, size_t e) {
 
 struct result_blob { std::vector<uint32_t> w; };
 
+const char* str_arg_of (int argc, char** argv, const char* key) {
+    const size_t n = strlen(key);
+    for (int i = 4; i < argc; ++i)
+        if (!strncmp(argv[i], key, n) && argv[i][n] == '=') return argv[i] + n + 1;
+    return nullptr;
+}
+
 long arg_of (int argc, char** argv, const char* key, long dflt) {
     const size_t n = strlen(key);
     for (int i = 4; i < argc; ++i)
@@ -87,6 +98,9 @@ int main (int argc, char** argv)
     const bool wantSk  = arg_of(argc, argv, "sketches", 1) != 0;
     const bool wantAll = arg_of(argc, argv, "allhits", 1) != 0;
     const bool dump    = outFile != "-";
+    const char* topsFile = str_arg_of(argc, argv, "tops");
+    const long first   = std::max(0L, arg_of(argc, argv, "first", 0));
+    const long count   = arg_of(argc, argv, "count", -1);
 
     const auto tload = std::chrono::steady_clock::now();
     database db = make_database(dbname, int(part), database::scope::everything,
@@ -104,7 +118,11 @@ int main (int argc, char** argv)
     {
         std::ifstream is(readsFile);
         std::string line;
+        long lineNo = -1;
         while (std::getline(is, line)) {
+            ++lineNo;
+            if (lineNo < first) continue;
+            if (count >= 0 && lineNo >= first + count) break;
             while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
             const auto sp = line.find(' ');
             read_pair r;
@@ -115,6 +133,7 @@ int main (int argc, char** argv)
     }
     const size_t n = reads.size();
     std::vector<result_blob> out(dump ? n : 0);
+    std::vector<uint32_t> tops(topsFile ? n * size_t(maxcand) * 4 : 0);
 
     auto work = [&] (size_t tid, bool record) {
         query_handler<location> handler;
@@ -124,6 +143,16 @@ int main (int argc, char** argv)
             seq_query q{r.s1, r.s2};
             auto rules = make_candidate_generation_rules(q, copt, skopt.winstride);
             db.query_host(r.s1, r.s2, handler, skopt, rules);
+            if (topsFile) {
+                uint32_t* t = tops.data() + i * size_t(maxcand) * 4;
+                size_t c = 0;
+                for (const auto& cand : handler.tophits()) {
+                    if (c >= size_t(maxcand)) break;
+                    t[4 * c] = cand.tgt; t[4 * c + 1] = cand.hits; t[4 * c + 2] = cand.pos.beg; t[4 * c + 3] = cand.pos.end;
+                    ++c;
+                }
+                for (; c < size_t(maxcand); ++c) { t[4 * c] = 0xFFFFFFFFu; t[4 * c + 1] = t[4 * c + 2] = t[4 * c + 3] = 0; }
+            }
             if (!record) continue;
             auto& w = out[i].w;
             if (wantSk) {
@@ -173,6 +202,12 @@ int main (int argc, char** argv)
         const uint32_t hdr[2] = {0x4d435246u, uint32_t(n)};
         fwrite(hdr, 4, 2, f);
         for (const auto& b : out) fwrite(b.w.data(), 4, b.w.size(), f);
+        fclose(f);
+    }
+    if (topsFile) {
+        FILE* f = fopen(topsFile, "wb");
+        if (!f) { std::cerr << "cannot write " << topsFile << "\n"; return 1; }
+        fwrite(tops.data(), 4, tops.size(), f);
         fclose(f);
     }
     printf("reads=%zu threads=%ld seconds=%.6f reads_per_s=%.1f load_seconds=%.3f\n",

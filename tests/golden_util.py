@@ -73,3 +73,19 @@ class G3:
 
     def expected(self, gi):
         return Expected(self.z, f"g{gi}_")
+
+
+def need_c1(gpu_test=False):
+    """The reference's bundled test data (oracle/_ref/c1: reference-built `bacteria1` database, reads and
+    classified.expected; made by __graft_entry__.build() from /root/reference, shipped to the GPU box with
+    the snapshot).  Its absence is a FAILURE wherever it can exist: in a GPU test (the artefact travels)
+    and in any environment that has the reference sources; only a CPU-only checkout without the reference
+    may skip."""
+    import os
+    import pytest
+    if os.path.exists(os.path.join(C1, "classified.expected")) and os.path.exists(os.path.join(C1, "bacteria1.cache0")):
+        return
+    if gpu_test or os.path.exists("/root/reference/src/main.cpp"):
+        pytest.fail("oracle/_ref/c1 is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
+                    "/root/reference exists (the parity test against the reference's golden file must not vanish)")
+    pytest.skip("oracle/_ref/c1 not built and no reference sources here")

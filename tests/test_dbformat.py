@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from metacache_b200 import dbformat
-from tests.golden_util import C1, G1
+from tests.golden_util import C1, need_c1, G1
 
 
 def test_cache_round_trip(tmp_path):
@@ -45,8 +45,8 @@ def test_meta_round_trip_synthetic(tmp_path):
     assert back.max_locations_per_feature == 254
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "bacteria1.meta")), reason="oracle/_ref/c1 not built")
 def test_reference_meta_byte_exact_round_trip(tmp_path):
+    need_c1()
     src = os.path.join(C1, "bacteria1.meta")
     meta = dbformat.read_meta(src)
     assert meta.target_count == 20 and meta.num_parts == 1

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden_util import C1, G1, G2, kat
+from tests.golden_util import C1, need_c1, G1, G2, kat
 
 pytestmark = pytest.mark.gpu
 
@@ -194,10 +194,9 @@ def test_random_reads_against_oracle(g1):
         assert res[i][1] == top, i
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
-                    reason="oracle/_ref/c1 not present (built from /root/reference by build())")
 def test_c1_bundled_database_matches_reference_golden_file():
     """BASELINE config C1: reference-built `bacteria1` + bundled reads vs classified.expected"""
+    need_c1(gpu_test=True)
     from metacache_b200 import formatting
     from metacache_b200.database import Database, query_reads
     from oracle import refio

@@ -1,6 +1,10 @@
 """Parity at benchmark scale: seeded synthetic workloads (BASELINE C2 recipe) checked through
 size-independent properties on every read, and bit-exactly against the oracle on a sample."""
 import ctypes as C
+import os
+import shutil
+import subprocess
+import tempfile
 
 import numpy as np
 import pytest
@@ -11,7 +15,7 @@ SK = dict(kmerlen=16, sketchlen=16, winlen=127, winstride=112)
 RL, MAXC = 150, 2
 
 
-def _build(n_targets, target_len, device):
+def _build(n_targets, target_len, device, want_windows=False):
     import torch
     from metacache_b200 import _lib, synth
     from metacache_b200._lib import Sketching
@@ -19,9 +23,12 @@ def _build(n_targets, target_len, device):
     bases, off = synth.make_targets(n_targets, target_len, 10, synth.SEED_DB, device=device)
     db = Database(device.index, 1)
     sk = Sketching(**SK)
+    wins = np.zeros(n_targets, np.uint32)
     _lib.check(_lib.lib().mcb200_db_build_part_from_targets(db._h, 0, bases.data_ptr(), off.data_ptr(), n_targets, 0,
-                                                            C.byref(sk), 254, 0.0, None))
+                                                            C.byref(sk), 254, 0.0, wins.ctypes.data))
     torch.cuda.synchronize(device)
+    if want_windows:
+        return db, bases, wins
     return db, bases
 
 
@@ -117,18 +124,58 @@ def test_medium_scale_properties_and_oracle_sample():
     db.close()
 
 
-def test_full_scale_c2_properties():
-    """BASELINE config C2 at full size: 10 M reads vs 50 k targets (714 M locations)"""
+def _reference_tops(db, wins, reads_np, tmp, first=0):
+    """top candidates of `reads_np` ([n, RL] uint8) from the REFERENCE's own hot path: the part is
+    exported to the reference's .meta/.cache0 format and queried by oracle/_ref/mc_ref_harness
+    (unmodified reference objects, database::query_host) on all host threads"""
+    from metacache_b200 import dbformat
+    from oracle import refio
+    assert os.path.exists(refio.HARNESS), "oracle/_ref/mc_ref_harness missing: run build() where /root/reference exists"
+    base = os.path.join(tmp, "db")
+    keys, sizes, values = db.export_part(0)
+    dbformat.write_cache(base + ".cache0", dbformat.CachePart(keys, sizes, values))
+    dbformat.write_meta(base + ".meta", dbformat.synthetic_meta(wins, **SK))
+    del keys, sizes, values
+    rt = os.path.join(tmp, "reads.txt")
+    lines = np.full((reads_np.shape[0], RL + 1), ord("\n"), np.uint8)
+    lines[:, :RL] = reads_np
+    lines.tofile(rt)
+    tops = os.path.join(tmp, "tops.bin")
+    refio.run_harness(base, rt, "-", threads=os.cpu_count() or 1, repeat=1, sketches=0, allhits=0, maxcand=MAXC, tops=tops)
+    ref = np.fromfile(tops, dtype="<u4").reshape(-1, MAXC, 4)
+    for f in (base + ".cache0", base + ".meta", rt, tops):
+        os.unlink(f)
+    return ref
+
+
+def _scratch_dir():
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    return tempfile.mkdtemp(prefix="mcb200_scale_", dir=d)
+
+
+def test_full_scale_c2_properties_and_reference_sample():
+    """BASELINE config C2 at full size: 10 M reads vs 50 k targets (714 M locations).  Properties on
+    every read, and the first 400 k reads bit-exactly against the reference's own hot path on the very
+    same full-size database (the headline configuration was only property-checked)."""
     import torch
     from metacache_b200 import synth
     device = torch.device("cuda", 0)
     NT, TL, NQ = 50_000, 100_000, 10_000_000
-    db, bases = _build(NT, TL, device)
+    db, bases, wins = _build(NT, TL, device, want_windows=True)
     assert db.value_count(0) == 714_400_000
     reads = synth.make_reads_150(NQ, bases, NT, TL, RL, device=device)
     del bases
     top = _query_device(db, reads, device)
     _check_properties(top, NT)
+    NREF = 400_000
+    tmp = _scratch_dir()
+    try:
+        ref = _reference_tops(db, wins, reads[:NREF].cpu().numpy(), tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    bad = np.flatnonzero((ref != top[:NREF]).any(axis=(1, 2)))
+    assert len(bad) == 0, (len(bad), int(bad[0]), ref[bad[0]].tolist(), top[bad[0]].tolist())
+    assert (ref[:, 0, 1] >= 5).mean() > 0.85
     # checksum of checksums: a second pass over the two halves in swapped order gives the same rows
     half = NQ // 2
     swapped = torch.cat([reads[half:], reads[:half]])
@@ -190,4 +237,49 @@ def test_long_reads_c3_properties_and_oracle_sample():
         _, want = O.query(tab, flat_np[offs_np[i]:offs_np[i + 1]].tobytes(), b"")
         got = [tuple(int(x) for x in row) for row in top[i] if row[1] > 0]
         assert got == want, (i, int(lens_np[i]))
+    db.close()
+
+
+def test_device_builder_matches_reference_build_on_1000_dbs_targets():
+    """The database both bench arms query is made by mcb200_db_build_part_from_targets.  Here the same
+    DB-S recipe, 1 000 targets x 100 kbp (14.3 M locations), is ALSO built by the reference's own
+    `metacache build` from a FASTA file of the same sequences: keys, bucket sizes and every bucket's
+    (tgt,win)-ordered location list must be identical (equivalence had only been checked on
+    a 16-target FASTA)."""
+    import torch
+    from metacache_b200 import dbformat, synth
+    from oracle import refio
+    assert os.path.exists(refio.METACACHE), "oracle/_ref/metacache missing: run build() where /root/reference exists"
+    device = torch.device("cuda", 0)
+    NT, TL = 1000, 100_000
+    db, bases, wins = _build(NT, TL, device, want_windows=True)
+    keys, sizes, values = db.export_part(0)
+    tmp = _scratch_dir()
+    try:
+        fa = os.path.join(tmp, "t.fa")
+        seqs = bases.cpu().numpy().reshape(NT, TL)
+        with open(fa, "wb") as f:
+            for i in range(NT):
+                f.write(b">t%d\n" % i)
+                f.write(seqs[i].tobytes())
+                f.write(b"\n")
+        subprocess.check_call([refio.METACACHE, "build", os.path.join(tmp, "ref"), fa, "-parts", "1", "-silent"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ref = dbformat.read_cache(os.path.join(tmp, "ref.cache0"))
+        meta = dbformat.read_meta(os.path.join(tmp, "ref.meta"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    assert meta.target_count == NT and np.array_equal(np.asarray(meta.target_windows(), np.uint32), wins)
+    assert len(keys) == len(ref.keys) and len(values) == len(ref.values) and len(values) > 14_000_000
+    o, ro = np.argsort(keys), np.argsort(ref.keys)
+    assert np.array_equal(keys[o], ref.keys[ro]) and np.array_equal(sizes[o], ref.sizes[ro])
+    # location lists in key order: gather both value arrays bucket by bucket
+    def by_key(sz, vals, order):
+        offs = np.zeros(len(sz) + 1, np.int64)
+        np.cumsum(sz, out=offs[1:])
+        lens = sz[order].astype(np.int64)
+        start = np.repeat(offs[:-1][order], lens)
+        within = np.arange(lens.sum(), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+        return vals[start + within]
+    assert np.array_equal(by_key(sizes, values, o), by_key(ref.sizes, ref.values, ro))
     db.close()

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import mc_oracle as O
-from tests.golden_util import C1, G1, G2, kat
+from tests.golden_util import C1, need_c1, G1, G2, kat
 
 
 def test_kat_hash_and_revcomp():
@@ -86,10 +86,9 @@ def test_candidates_tie_breaks_and_ranges():
     assert O.candidates(locs + [loc(3, 8)], 3, 2, tax) == [(3, 3, 7, 8), (2, 2, 1, 1)]
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
-                    reason="oracle/_ref/c1 not built (needs /root/reference)")
 def test_oracle_matches_reference_golden_file():
     """oracle vs the reference's OWN golden test/data/classified.expected (single.fa section)."""
+    need_c1()
     from metacache_b200 import dbformat, formatting
     from oracle import refio
     meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
@@ -121,10 +120,9 @@ def test_oracle_matches_reference_golden_file():
     assert checked > 10000
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(C1, "classified.expected")),
-                    reason="oracle/_ref/c1 not built (needs /root/reference)")
 def test_oracle_classification_matches_reference_golden_file():
     """classify() restatement vs the last column of classified.expected (all three sections)"""
+    need_c1()
     from metacache_b200 import dbformat, formatting
     from metacache_b200.database import Database
     from metacache_b200.statistics import ClassificationStatistics

@@ -79,9 +79,9 @@ def test_byte_ranges_partition_the_records(name, nranges, tmp_path):
 
 def test_bundled_reference_reads_if_present():
     """the reads of the reference's own test suite (present where oracle/_ref/c1 was unpacked)"""
+    from tests.golden_util import need_c1
+    need_c1()
     c1 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "c1")
-    if not os.path.exists(os.path.join(c1, "single.fa")):
-        pytest.skip("oracle/_ref/c1 not unpacked")
     with SequenceReader(os.path.join(c1, "single.fa")) as r:
         n = sum(1 for _ in r)
     heads = sum(1 for line in open(os.path.join(c1, "single.fa"), "rb") if line.startswith(b">"))
