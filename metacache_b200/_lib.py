@@ -167,3 +167,18 @@ def check_ptr(p):
     if not p:
         raise Mcb200Error(None, lib().mcb200_last_error().decode(errors="replace"))
     return p
+
+
+def query_device_checked(ws, q, sk, d_top_ptr, stream=None, max_attempts=6):
+    """mcb200_query_device followed by mcb200_workspace_check, re-issued while the library answers
+    MCB200_EAGAIN (a read outgrew its scratch region and the pool was grown).  Synchronises the stream.
+    Returns the number of attempts."""
+    L = lib()
+    for attempt in range(1, max_attempts + 1):
+        check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), d_top_ptr, stream))
+        rc = L.mcb200_workspace_check(ws)
+        if rc == EAGAIN:
+            continue
+        check(rc)
+        return attempt
+    raise Mcb200Error(EAGAIN, "scratch pool still too small after %d attempts" % max_attempts)

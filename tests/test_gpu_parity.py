@@ -287,8 +287,15 @@ def test_fast_kernel_small_table_overflows_to_cta_kernel(g1):
     q = _lib.DevQueries(t_b.data_ptr(), t_o.data_ptr(), t_q.data_ptr(), t_w.data_ptr(), ns, nq, nb)
     sk = _sk(g1).c()
     top = torch.empty((nq, 2, 4), dtype=torch.int32, device=dev)
+    # the 19 kbp tandem-repeat read of g1 gathers 690 k locations: more than a CTA's region of the
+    # default scratch pool.  The asynchronous device API must not lose it silently:
+    # the check after the call reports MCB200_EAGAIN (pool grown), the re-issued call is complete.
     _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top.data_ptr(), None))
+    assert L.mcb200_workspace_check(ws) == _lib.EAGAIN
+    assert b"scratch pool grown" in L.mcb200_last_error()
     cnt = (C.c_uint64 * 8)()
+    _lib.check(L.mcb200_workspace_counters(ws, cnt))             # resets the counters of the incomplete attempt
+    assert _lib.query_device_checked(ws, q, sk, top.data_ptr()) == 1
     _lib.check(L.mcb200_workspace_counters(ws, cnt))
     assert cnt[0] + cnt[1] + cnt[2] == nq and cnt[1] > 0 and cnt[2] > 0
     got = top.cpu().numpy().astype(np.uint32)

@@ -47,8 +47,7 @@ def _query_device(db, reads, device):
     q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), nq, nq, nq * RL)
     sk = Sketching(**SK)
     top = torch.empty((nq, MAXC, 4), dtype=torch.int32, device=device)
-    _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top.data_ptr(), None))
-    torch.cuda.synchronize(device)
+    _lib.query_device_checked(ws, q, sk, top.data_ptr())
     out = top.cpu().numpy().view(np.uint32)
     L.mcb200_workspace_destroy(ws)
     return out
@@ -209,8 +208,7 @@ def test_long_reads_c3_properties_and_oracle_sample():
     q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), NQ, NQ, n_bases)
     sk = Sketching(**SK)
     top_d = torch.empty((NQ, MAXC, 4), dtype=torch.int32, device=device)
-    _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top_d.data_ptr(), None))
-    torch.cuda.synchronize(device)
+    _lib.query_device_checked(ws, q, sk, top_d.data_ptr())
     cnt = (C.c_uint64 * 8)()
     _lib.check(L.mcb200_workspace_counters(ws, cnt))
     top = top_d.cpu().numpy().view(np.uint32)
