@@ -168,8 +168,13 @@ int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const char* base
                                 const uint64_t* offsets, uint32_t n_queries, int paired,
                                 uint64_t insert_size_max, uint32_t winstride);
 
-/* database::query_gpu_async -> gpu_hashmap::query_async (asynchronous):
- * H2D copy, encode, sketch, probe + candidate generation on every part,
+/* The adding thread packs the bases while it copies them into the slot's pinned
+ * buffers (2 bits per base + 1 ambiguity bit, see mcb200_pack_bases), so a slot
+ * ships 0.375 B/base to the device instead of the characters the reference ships
+ * (query_batch.cuh:131-160 copies the window characters, the device encodes).
+ *
+ * database::query_gpu_async -> gpu_hashmap::query_async (asynchronous):
+ * H2D copy, sketch, probe + candidate generation on every part,
  * part-ordered merge, D2H copy of the results - all on the slot's stream.    */
 int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200_sketching* sk);
 /* query_host_data::wait_for_results (query_batch.cu:147)                     */
@@ -252,6 +257,29 @@ int mcb200_merge_candidates_device (mcb200_workspace* ws, const mcb200_candidate
  * merge -> d_top.                                                            */
 int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
                          const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream);
+
+/* Host-side packing of bases into the device layout (what the batch slots do
+ * while reads are added; encode_kernel produces the same words from ASCII on the
+ * device; dna_encoding.hpp:38-62, 270-316): appends n bases at batch position
+ * `pos` (bases of a batch are numbered back to back across reads).
+ *   codes: u32 words of 16 bases, first base in the top two bits, A0 C1 G2 T3
+ *          (U = T, lower case folded), ambiguous bases 0
+ *   amb:   u32 words of 32 bases, first base in the top bit, 1 = not ACGTU
+ * Appends must come in ascending `pos` order without gaps, starting at a multiple
+ * of 32: a call ORs into the word it starts in and stores every further word.
+ * Room needed: codes[2 * ((pos + n + 31) / 32 + 1)], amb[(pos + n + 31) / 32 + 1].
+ * Before shipping, set the bits of the last amb word beyond the final base.
+ * Returns 1 if the AVX2 path ran, 0 for the scalar one, < 0 on error.          */
+int mcb200_pack_bases (const char* bases, uint64_t n, uint64_t pos, uint32_t* codes, uint32_t* amb);
+/* mcb200_sketch_device / mcb200_query_device for reads that are ALREADY packed in
+ * device memory (layout above; 16-byte aligned, 64 readable bytes behind the last
+ * word, bits beyond n_bases in the last amb word set): q->bases is ignored.    */
+int mcb200_sketch_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                 const uint32_t* d_codes, const uint32_t* d_amb,
+                                 const mcb200_sketching* sk, void* stream);
+int mcb200_query_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                const uint32_t* d_codes, const uint32_t* d_amb,
+                                const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream);
 
 /* classify() on the device for n_queries candidate lists (d_top as produced by
  * the query entry points): LCA over the ranked lineages of the candidates whose

@@ -124,6 +124,9 @@ _SIGS = {
     "mcb200_query_sketches_device": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_merge_candidates_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_query_device": (C.c_int, [_P, C.POINTER(DevQueries), C.POINTER(Sketching), _P, _P]),
+    "mcb200_pack_bases": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P]),
+    "mcb200_sketch_packed_device": (C.c_int, [_P, C.POINTER(DevQueries), _P, _P, C.POINTER(Sketching), _P]),
+    "mcb200_query_packed_device": (C.c_int, [_P, C.POINTER(DevQueries), _P, _P, C.POINTER(Sketching), _P, _P]),
     "mcb200_workspace_num_windows": (C.c_uint32, [_P]),
     "mcb200_workspace_sketches": (_P, [_P]),
     "mcb200_workspace_query_windows": (_P, [_P]),

@@ -485,8 +485,9 @@ extern "C" int mcb200_workspace_stage_times (mcb200_workspace* ws, float ms[8]) 
     return 0;
 }
 
-extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
-                                     const mcb200_sketching* sk, void* stream) {
+// packed input (mcb200_pack_bases layout) when d_codes/d_amb are given, else q->bases is encoded first
+static int sketch_impl (mcb200_workspace* ws, const mcb200_dev_queries* q, const mcb200_sketching* sk,
+                        void* stream, const uint32_t* d_codes, const uint32_t* d_amb) {
     if (!ws || !q) return fail(MCB200_EINVAL, "null argument");
     int rc = validate_sketching(sk);
     if (rc) return rc;
@@ -495,7 +496,15 @@ extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_quer
                     q->n_queries, ws->max_queries, q->n_seqs, ws->max_seqs,
                     (unsigned long long)q->n_bases, (unsigned long long)ws->max_bases);
     if (q->n_seqs < q->n_queries) return fail(MCB200_EINVAL, "every query needs at least one sequence");
-    if (reinterpret_cast<uintptr_t>(q->bases) & 15) return fail(MCB200_EINVAL, "bases must be 16-byte aligned");
+    const bool packed = d_codes != nullptr;
+    if (packed) {
+        if (!d_amb) return fail(MCB200_EINVAL, "packed input needs both the codes and the ambiguity bits");
+        if ((reinterpret_cast<uintptr_t>(d_codes) | reinterpret_cast<uintptr_t>(d_amb)) & 15)
+            return fail(MCB200_EINVAL, "packed bases must be 16-byte aligned");
+    } else {
+        if (!q->bases && q->n_bases) return fail(MCB200_EINVAL, "null bases");
+        if (reinterpret_cast<uintptr_t>(q->bases) & 15) return fail(MCB200_EINVAL, "bases must be 16-byte aligned");
+    }
     CU(cudaSetDevice(ws->db->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ws->q = *q; ws->sk = SketchParams{sk->kmerlen, sk->sketchlen, sk->winlen, sk->winstride};
@@ -511,7 +520,7 @@ extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_quer
     CU(ws->feats.ensure(bound * sk->sketchlen));
 
     if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; CU(cudaEventRecord(ws->ev->sk[0], st)); }
-    launch_encode(q->bases, q->n_bases, ws->codes.p, ws->amb.p, st);
+    if (!packed) { launch_encode(q->bases, q->n_bases, ws->codes.p, ws->amb.p, st); d_codes = ws->codes.p; d_amb = ws->amb.p; }
     if (ws->profiling) CU(cudaEventRecord(ws->ev->sk[1], st));
     launch_count_windows(q->seq_offsets, q->n_seqs, ws->sk, ws->seq_nwin.p, st);
     CU(cudaMemsetAsync(ws->seq_nwin.p + q->n_seqs, 0, 4, st));
@@ -519,12 +528,23 @@ extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_quer
     launch_fill_windows(ws->seq_win_off.p, q->seq_query, q->n_seqs, q->n_queries, ws->win_seq.p,
                         ws->qry_win_off.p, st);
     if (ws->profiling) CU(cudaEventRecord(ws->ev->sk[2], st));
-    launch_sketch(ws->codes.p, ws->amb.p, q->seq_offsets, ws->seq_win_off.p, ws->win_seq.p,
+    launch_sketch(d_codes, d_amb, q->seq_offsets, ws->seq_win_off.p, ws->win_seq.p,
                   ws->seq_win_off.p + q->n_seqs, ws->sk, ws->feats.p, ws->db->sm_count, st);
     if (ws->profiling) { CU(cudaEventRecord(ws->ev->sk[3], st)); ws->ev->sketched = true; }
     CU(cudaGetLastError());
     ws->sketched = true;
     return 0;
+}
+
+extern "C" int mcb200_sketch_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                     const mcb200_sketching* sk, void* stream) {
+    return sketch_impl(ws, q, sk, stream, nullptr, nullptr);
+}
+extern "C" int mcb200_sketch_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                            const uint32_t* d_codes, const uint32_t* d_amb,
+                                            const mcb200_sketching* sk, void* stream) {
+    if (!d_codes || !d_amb) return fail(MCB200_EINVAL, "null packed bases");
+    return sketch_impl(ws, q, sk, stream, d_codes, d_amb);
 }
 
 static int ensure_scratch (mcb200_workspace* ws, uint64_t entries) {
@@ -679,12 +699,13 @@ __global__ void part_offsets_kernel (const uint64_t* __restrict__ offs, uint64_t
     if (q < nq) out[q] = offs[uint64_t(q) * np + p];
 }
 
-extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
-                                    const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream) {
+static int query_device_impl (mcb200_workspace* ws, const mcb200_dev_queries* q, const uint32_t* d_codes,
+                              const uint32_t* d_amb, const mcb200_sketching* sk, mcb200_candidate* d_top,
+                              void* stream) {
     if (!ws || !q || !d_top) return fail(MCB200_EINVAL, "null argument");
     for (auto& p : ws->db->parts) if (!p.finished) return fail(MCB200_ESTATE, "database part not loaded");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = mcb200_sketch_device(ws, q, sk, stream);
+    int rc = sketch_impl(ws, q, sk, stream, d_codes, d_amb);
     if (rc) return rc;
     const uint32_t np = uint32_t(ws->db->parts.size());
     const uint32_t nq = q->n_queries;
@@ -739,6 +760,17 @@ extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queri
         if (rc != MCB200_EAGAIN) return rc;
     }
     return fail(MCB200_ENOMEM, "scratch pool exhausted");
+}
+
+extern "C" int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                    const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream) {
+    return query_device_impl(ws, q, nullptr, nullptr, sk, d_top, stream);
+}
+extern "C" int mcb200_query_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
+                                           const uint32_t* d_codes, const uint32_t* d_amb,
+                                           const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream) {
+    if (!d_codes || !d_amb) return fail(MCB200_EINVAL, "null packed bases");
+    return query_device_impl(ws, q, d_codes, d_amb, sk, d_top, stream);
 }
 
 extern "C" int mcb200_workspace_set_warp_capacity (mcb200_workspace* ws, uint32_t cap) {
@@ -923,12 +955,23 @@ extern "C" int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
     return mcb200_db_part_finish(db, part);
 }
 
+// pack.cpp
+extern "C" int mcb200_internal_pack_has_avx2 (void);
+extern "C" void mcb200_internal_pack_append (const char* bases, uint64_t n, uint64_t pos,
+                                             uint32_t* codes, uint32_t* amb, int force_scalar);
+extern "C" int mcb200_pack_bases (const char* bases, uint64_t n, uint64_t pos, uint32_t* codes, uint32_t* amb) {
+    if ((n && !bases) || !codes || !amb) return fail(MCB200_EINVAL, "null argument");
+    mcb200_internal_pack_append(bases, n, pos, codes, amb, 0);
+    return mcb200_internal_pack_has_avx2();
+}
+
 // ---------------------------------------------------------------------------
 // query batch (host buffers)
 // ---------------------------------------------------------------------------
 struct Slot_ {
-    PinBuf<char> h_bases; PinBuf<uint32_t> h_seq_off, h_seq_query, h_max_win;
-    DevBuf<char> d_bases; DevBuf<uint32_t> d_seq_off, d_seq_query, d_max_win;
+    PinBuf<uint32_t> h_codes, h_amb;      // 2-bit bases + ambiguity bits, packed by the filling thread (pack.cpp)
+    PinBuf<uint32_t> h_seq_off, h_seq_query, h_max_win;
+    DevBuf<uint32_t> d_seq_off, d_seq_query, d_max_win;
     DevBuf<mcb200_candidate> d_top; PinBuf<mcb200_candidate> h_top;
     DevBuf<mcb200_classification> d_cls; PinBuf<mcb200_classification> h_cls; bool has_cls = false;
     PinBuf<uint32_t> h_feats, h_qry_win_off; PinBuf<uint64_t> h_allhits, h_allhits_off;
@@ -962,9 +1005,10 @@ extern "C" mcb200_batch* mcb200_batch_create (mcb200_db* db, uint32_t max_querie
     for (auto& s : b->slots) {
         cudaError_t e = cudaSuccess;
         auto ok = [&] (cudaError_t x) { if (e == cudaSuccess) e = x; };
-        ok(s.h_bases.ensure(max_bases + 64)); ok(s.h_seq_off.ensure(max_seqs + 1));
+        const uint64_t units = (max_bases + 31) / 32 + 2;
+        ok(s.h_codes.ensure(units * 2)); ok(s.h_amb.ensure(units)); ok(s.h_seq_off.ensure(max_seqs + 1));
         ok(s.h_seq_query.ensure(max_seqs)); ok(s.h_max_win.ensure(max_queries));
-        ok(s.d_bases.ensure(max_bases + 64)); ok(s.d_seq_off.ensure(max_seqs + 1));
+        ok(s.d_seq_off.ensure(max_seqs + 1));
         ok(s.d_seq_query.ensure(max_seqs)); ok(s.d_max_win.ensure(max_queries));
         ok(s.d_top.ensure(uint64_t(max_queries) * max_candidates));
         ok(s.h_top.ensure(uint64_t(max_queries) * max_candidates));
@@ -987,8 +1031,8 @@ extern "C" void mcb200_batch_destroy (mcb200_batch* b) {
     cudaSetDevice(b->db->device);
     for (auto& s : b->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        s.h_bases.release(); s.h_seq_off.release(); s.h_seq_query.release(); s.h_max_win.release();
-        s.d_bases.release(); s.d_seq_off.release(); s.d_seq_query.release(); s.d_max_win.release();
+        s.h_codes.release(); s.h_amb.release(); s.h_seq_off.release(); s.h_seq_query.release(); s.h_max_win.release();
+        s.d_seq_off.release(); s.d_seq_query.release(); s.d_max_win.release();
         s.d_top.release(); s.h_top.release(); s.h_feats.release(); s.h_qry_win_off.release();
         s.d_cls.release(); s.h_cls.release();
         s.h_allhits.release(); s.h_allhits_off.release();
@@ -1006,23 +1050,30 @@ extern "C" void mcb200_batch_destroy (mcb200_batch* b) {
     if (!(b)) return fail(MCB200_EINVAL, "null batch handle"); \
     if ((slot) >= (b)->slots.size()) return fail(MCB200_EINVAL, "slot %u out of range", unsigned(slot));
 
-static inline bool slot_add (mcb200_batch* b, Slot_& s, const char* s1, uint64_t l1, const char* s2,
-                             uint64_t l2, uint32_t max_win) {
+// registers a read (one or two sequences) in the slot's tables; the caller packs the bases
+static inline bool slot_add_meta (mcb200_batch* b, Slot_& s, uint64_t l1, uint64_t l2, uint32_t max_win) {
     const uint32_t max_seqs = uint32_t(s.h_seq_query.n);
     const uint32_t nseq = (l2 > 0) ? 2u : 1u;
     if (s.n_queries + 1 > b->max_queries || s.n_seqs + nseq > max_seqs ||
         s.n_bases + l1 + l2 > b->max_bases) return false;
-    memcpy(s.h_bases.p + s.n_bases, s1, l1);
     s.n_bases += l1;
     s.h_seq_query.p[s.n_seqs] = s.n_queries;
     s.h_seq_off.p[++s.n_seqs] = uint32_t(s.n_bases);
     if (l2 > 0) {
-        memcpy(s.h_bases.p + s.n_bases, s2, l2);
         s.n_bases += l2;
         s.h_seq_query.p[s.n_seqs] = s.n_queries;
         s.h_seq_off.p[++s.n_seqs] = uint32_t(s.n_bases);
     }
     s.h_max_win.p[s.n_queries++] = max_win;
+    return true;
+}
+
+static inline bool slot_add (mcb200_batch* b, Slot_& s, const char* s1, uint64_t l1, const char* s2,
+                             uint64_t l2, uint32_t max_win) {
+    const uint64_t pos = s.n_bases;
+    if (!slot_add_meta(b, s, l1, l2, max_win)) return false;
+    mcb200_internal_pack_append(s1, l1, pos, s.h_codes.p, s.h_amb.p, 0);
+    if (l2 > 0) mcb200_internal_pack_append(s2, l2, pos + l1, s.h_codes.p, s.h_amb.p, 0);
     return true;
 }
 
@@ -1045,20 +1096,27 @@ extern "C" int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const
     Slot_& s = b->slots[slot];
     if (s.submitted) return fail(MCB200_ESTATE, "slot %u: clear() before adding reads again", slot);
     if (!bases || !offsets || winstride == 0) return fail(MCB200_EINVAL, "bad argument");
+    // the reads are contiguous in `bases` (an empty mate contributes nothing): register them one by
+    // one, then pack the whole base range with one call
     int64_t added = 0;
+    const uint64_t pos = s.n_bases;
+    const uint64_t first = offsets[0];
+    uint64_t last = first;
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint64_t o0 = offsets[paired ? 2 * uint64_t(i) : i];
         const uint64_t o1 = offsets[(paired ? 2 * uint64_t(i) : i) + 1];
         const uint64_t o2 = paired ? offsets[2 * uint64_t(i) + 2] : o1;
+        if (o0 != last || o1 < o0 || o2 < o1) return fail(MCB200_EINVAL, "offsets must ascend without gaps");
         const uint64_t l1 = o1 - o0, l2 = o2 - o1;
         // make_candidate_generation_rules (candidate_structs.hpp:134-151)
         const uint32_t mw = uint32_t(2 + std::max<uint64_t>(l1 + l2, insert_size_max) / winstride);
-        bool ok;
-        if (l1 == 0 && l2 > 0) ok = slot_add(b, s, bases + o1, l2, nullptr, 0, mw);
-        else ok = slot_add(b, s, bases + o0, l1, bases + o1, l2, mw);
+        // a read with an empty first mate keeps its (non-empty) second mate as only sequence
+        const bool ok = (l1 == 0 && l2 > 0) ? slot_add_meta(b, s, l2, 0, mw) : slot_add_meta(b, s, l1, l2, mw);
         if (!ok) break;
+        last = o2;
         ++added;
     }
+    mcb200_internal_pack_append(bases + first, last - first, pos, s.h_codes.p, s.h_amb.p, 0);
     return added;
 }
 
@@ -1073,15 +1131,17 @@ extern "C" int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200
     s.sub_queries = s.n_queries; s.sub_s = sk->sketchlen;
     CU(cudaEventRecord(s.ev_start, st));
     if (s.n_queries == 0) { CU(cudaEventRecord(s.ev_k0, st)); CU(cudaEventRecord(s.ev_k1, st)); CU(cudaEventRecord(s.ev_done, st)); return 0; }
-    const uint64_t nb_pad = (s.n_bases + 15) & ~15ull;
-    memset(s.h_bases.p + s.n_bases, 0, nb_pad - s.n_bases);
-    CU(cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, nb_pad, cudaMemcpyHostToDevice, st));
+    // bases beyond the last one count as ambiguous (encode_kernel does the same for its tail)
+    const uint64_t units = (s.n_bases + 31) / 32;
+    if (s.n_bases & 31u) s.h_amb.p[units - 1] |= 0xFFFFFFFFu >> (s.n_bases & 31u);
+    CU(cudaMemcpyAsync(s.ws->codes.p, s.h_codes.p, units * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.ws->amb.p, s.h_amb.p, units * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s.d_seq_off.p, s.h_seq_off.p, (uint64_t(s.n_seqs) + 1) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s.d_seq_query.p, s.h_seq_query.p, uint64_t(s.n_seqs) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s.d_max_win.p, s.h_max_win.p, uint64_t(s.n_queries) * 4, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(s.ev_k0, st));
-    mcb200_dev_queries q{s.d_bases.p, s.d_seq_off.p, s.d_seq_query.p, s.d_max_win.p, s.n_seqs, s.n_queries, s.n_bases};
-    rc = mcb200_query_device(s.ws, &q, sk, s.d_top.p, st);
+    mcb200_dev_queries q{nullptr, s.d_seq_off.p, s.d_seq_query.p, s.d_max_win.p, s.n_seqs, s.n_queries, s.n_bases};
+    rc = query_device_impl(s.ws, &q, s.ws->codes.p, s.ws->amb.p, sk, s.d_top.p, st);
     if (rc) return rc;
     s.has_cls = false;
     if (b->cls_hits_min > 0 && b->db->d_lineages) {

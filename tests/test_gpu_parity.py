@@ -548,3 +548,66 @@ def test_other_geometries_match_reference(gi):
         assert top == exp.top[i], i
     qb.close()
     db.close()
+
+
+def test_host_packed_bases_equal_device_encoding(g1):
+    """mcb200_pack_bases (host, csrc/pack.cpp) + mcb200_query_packed_device == encode_kernel +
+    mcb200_query_device on the edge-case reads of G1 (IUPAC, N runs, lower case, U, empty mates):
+    same sketches, same candidates."""
+    import ctypes as C
+    import torch
+    from metacache_b200 import _lib
+    from metacache_b200._lib import DevQueries, Sketching
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    seqs, seq_query = [], []
+    for qi, (a, b) in enumerate(g1.reads):
+        mates = [m for m in (a, b) if len(m)] or [b""]
+        for m in mates:
+            seqs.append(m)
+            seq_query.append(qi)
+    lens = np.array([len(s) for s in seqs], np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    flat = np.frombuffer(b"".join(seqs), np.uint8)
+    nq, ns, nb = len(g1.reads), len(seqs), int(offs[-1])
+    units = (nb + 31) // 32
+    codes = np.zeros(2 * (units + 1) + 16, np.uint32)
+    amb = np.zeros(units + 1 + 16, np.uint32)
+    pos = 0
+    for s in seqs:                                             # read by read: every bit offset occurs
+        buf = np.frombuffer(s, np.uint8)
+        assert L.mcb200_pack_bases(buf.ctypes.data if len(buf) else None, len(buf), pos, codes.ctypes.data, amb.ctypes.data) >= 0
+        pos += len(buf)
+    if nb & 31:
+        amb[units - 1] |= np.uint32(0xFFFFFFFF >> (nb & 31))
+    pad = np.zeros(64, np.uint8)
+    d_flat = torch.from_numpy(np.concatenate([flat, pad])).to(dev)
+    d_codes, d_amb = torch.from_numpy(codes.view(np.int32)).to(dev), torch.from_numpy(amb.view(np.int32)).to(dev)
+    d_off = torch.from_numpy(offs.astype(np.uint32).view(np.int32)).to(dev)
+    d_sq = torch.from_numpy(np.array(seq_query, np.int32)).to(dev)
+    mw = np.array([2 + max(len(a) + len(b), 0) // g1.stride for a, b in g1.reads], np.int32)
+    d_mw = torch.from_numpy(mw).to(dev)
+    sk = Sketching(g1.k, g1.s, g1.w, g1.stride)
+    out = []
+    for packed in (False, True):
+        ws = _lib.check_ptr(L.mcb200_workspace_create(g1.db._h, nq, ns, nb + 64, 2, 0))
+        q = DevQueries(None if packed else d_flat.data_ptr(), d_off.data_ptr(), d_sq.data_ptr(), d_mw.data_ptr(), ns, nq, nb)
+        top = torch.empty((nq, 2, 4), dtype=torch.int32, device=dev)
+        for attempt in range(6):
+            if packed:
+                _lib.check(L.mcb200_query_packed_device(ws, C.byref(q), d_codes.data_ptr(), d_amb.data_ptr(),
+                                                        C.byref(sk), top.data_ptr(), None))
+            else:
+                _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), top.data_ptr(), None))
+            rc = L.mcb200_workspace_check(ws)
+            if rc != _lib.EAGAIN:
+                _lib.check(rc)
+                break
+        nw = L.mcb200_workspace_num_windows(ws)
+        from metacache_b200.distributed import _as_tensor
+        feats = _as_tensor(L.mcb200_workspace_sketches(ws), nw * g1.s, dev).cpu().numpy().copy()
+        out.append((top.cpu().numpy().copy(), feats))
+        L.mcb200_workspace_destroy(ws)
+    assert np.array_equal(out[0][1], out[1][1]), "sketches differ between device-encoded and host-packed bases"
+    assert np.array_equal(out[0][0], out[1][0])
+    assert (out[0][0][:, 0, 1] > 0).sum() > 100
