@@ -259,6 +259,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     h2d = sum(((int(host_offs[e] - host_offs[b]) + 31) // 32) * 12 + (e - b + 1) * 4 + (e - b) * 8 for b, e in chunks)
     d2h = nq * MAXC * 16
     errors = []
+    spent = [[0.0, 0.0, 0.0] for _ in range(T)]               # per worker: wait + collect | add (pack) | submit
 
     def collect(slot, ci):
         _lib.check(L.mcb200_batch_wait(qb, slot))
@@ -275,23 +276,32 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
             for _ in range(steps):
                 for ci in mine:
                     slot = 2 * t + (k & 1)
+                    t0 = time.perf_counter()
                     if pending[k & 1] is not None:
                         collect(slot, pending[k & 1])
                     _lib.check(L.mcb200_batch_clear(qb, slot))
+                    t1 = time.perf_counter()
                     b, e = chunks[ci]
                     added = _lib.check(L.mcb200_batch_add_reads(qb, slot, base_ptr + int(host_offs[b]),
                                                                 chunk_offs[ci].ctypes.data, e - b, 0, 0, SK["winstride"]))
                     assert added == e - b
+                    t2 = time.perf_counter()
                     _lib.check(L.mcb200_batch_submit(qb, slot, C.byref(sk)))
+                    t3 = time.perf_counter()
+                    spent[t][0] += t1 - t0; spent[t][1] += t2 - t1; spent[t][2] += t3 - t2
                     pending[k & 1] = ci
                     k += 1
+            t0 = time.perf_counter()
             for j in (0, 1):
                 if pending[(k + j) & 1] is not None:
                     collect(2 * t + ((k + j) & 1), pending[(k + j) & 1])
+            spent[t][0] += time.perf_counter() - t0
         except Exception as ex:                                   # surfaced by the caller
             errors.append(ex)
 
     def run(steps):
+        for x in spent:
+            x[:] = [0.0, 0.0, 0.0]
         start = threading.Barrier(T + 1)
         th = [threading.Thread(target=worker, args=(t, steps, start)) for t in range(T)]
         for x in th:
@@ -309,6 +319,8 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
 
     run(max(args.warmup, 3))
     wall_ms = run(args.steps) / args.steps
+    host_ms = {k_: round(1e3 * sum(x[i] for x in spent) / T / args.steps, 3)
+               for i, k_ in enumerate(("wait_results", "add_reads_pack", "submit"))}
     same = None
     if top_first is not None:
         n = min(len(top_first), nq)
@@ -338,7 +350,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     L.mcb200_batch_destroy(qb)
     return {"value": nq / (wall_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": round(wall_ms, 3), "timed_by": "wall clock, host work included",
-            "host_threads": T, "slots": nslots, "reads_per_slot": per,
+            "host_threads": T, "slots": nslots, "reads_per_slot": per, "host_ms_per_thread_per_step": host_ms,
             "results_equal_device_resident_path": same,
             "prefilled": {"value": nq / (pre_ms * 1e-3), "ms_per_step": round(pre_ms, 3),
                           "note": "slots filled (packed) before the timed region: pinned -> H2D -> kernels -> D2H only, "

@@ -281,6 +281,71 @@ int mcb200_query_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* 
                                 const uint32_t* d_codes, const uint32_t* d_amb,
                                 const mcb200_sketching* sk, mcb200_candidate* d_top, void* stream);
 
+/* ---- feature-space sharding over the GPUs of one box --------------------------
+ * Replaces the reference's multi-GPU query, where the database is partitioned by
+ * TARGET and every GPU looks every read up in its part (gpu_hashmap.cu:1255-1292,
+ * 1320-1362; query_batch.cu:464-527), by a partition of the FEATURE space: shard
+ * r of n holds the features f with owner(f) = r, each with the locations of ALL
+ * parts (buckets concatenated in part order).  A read costs one table access per
+ * feature however many GPUs hold the database; features travel to their owners and
+ * location lists travel back (one process per GPU exchanges them over NCCL, see
+ * metacache_b200/distributed.py; results equal the per-part query + part-ordered
+ * merge of docs/partitioning.md:116-142).
+ *
+ * Load: shard_begin(part slot, shard, n_shards), then feed EVERY part of the
+ * database in part order through the usual loaders on that slot
+ * (mcb200_db_part_begin/append/finish, mcb200_db_load_cache_file,
+ * mcb200_db_build_part_from_targets): they keep only the keys this shard owns.
+ * shard_finish merges the buckets and builds the table.  n_targets = targets of
+ * the whole database (.meta): the reference merges per-part candidate lists in
+ * part order, so on equal hits a target of an earlier part wins whatever its id;
+ * the shard learns each target's part from the locations it is fed and numbers
+ * targets part-major internally (candidates come back with the original ids).
+ * n_targets = 0 skips that: ids must then ascend with the part.  All shards must pack
+ * locations alike: pass the database-wide largest target and window id (each
+ * shard's own maxima from shard_maxima, reduced with max over the shards).       */
+int mcb200_db_shard_begin  (mcb200_db* db, uint32_t part, uint32_t shard, uint32_t n_shards,
+                            uint32_t n_targets);
+int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* max_target_id, uint32_t* max_window_id);
+int mcb200_db_shard_finish (mcb200_db* db, uint32_t part, float max_load_factor,
+                            uint32_t max_target_id, uint32_t max_window_id);
+/* bytes per location in the exchange buffers of this part: 4 (packed) or 8       */
+uint32_t mcb200_db_location_bytes (const mcb200_db* db, uint32_t part);
+
+/* origin: routes the sketches of n_queries reads (d_feats[window][sketchlen] padded
+ * with 0xFFFFFFFF, d_qry_win_off[n_queries + 1] = first window of every read: the
+ * workspace arrays after mcb200_sketch_device, or a sub-range of its reads).
+ * d_pos[n_shards * (n_queries + 1) + 1] = exclusive scan of the number of features
+ * of read q owned by shard o, at index o * (n_queries + 1) + q (the slice of shard
+ * o in the send buffer starts at d_pos[o * (n_queries + 1)], the last entry is the
+ * total); d_send_feats[<= windows * sketchlen] = the features grouped by owner,
+ * reads in order.  `ws` lends its scan scratch: one workspace per stream.         */
+int mcb200_shard_route_device (mcb200_workspace* ws, const uint32_t* d_feats,
+                               const uint32_t* d_qry_win_off, uint32_t n_queries, uint32_t sketchlen,
+                               uint32_t n_shards, uint32_t* d_pos, uint32_t* d_send_feats, void* stream);
+/* owner: looks up n received features: d_off[n + 1] = exclusive scan of the bucket
+ * sizes (d_off[n] = locations to return), d_data[n] = slot contents for gather   */
+int mcb200_shard_probe_device (mcb200_workspace* ws, uint32_t part, const uint32_t* d_feats, uint64_t n,
+                               uint32_t* d_off, uint64_t* d_data, void* stream);
+/* owner: d_locs[d_off[i] .. d_off[i + 1]) = the bucket of feature i
+ * (mcb200_db_location_bytes each, (tgt,win) order as stored)                      */
+int mcb200_shard_gather_device (mcb200_workspace* ws, uint32_t part, const uint32_t* d_off,
+                                const uint64_t* d_data, uint64_t n, void* d_locs, void* stream);
+/* origin: what owner o returned for the features sent to it (device pointers):
+ * offsets[i] = d_off of my i-th feature in the owner's numbering (only differences
+ * to offsets[0] are used), locations = the matching slice of its d_locs           */
+typedef struct mcb200_shard_run {
+    const void*     locations;
+    const uint32_t* offsets;
+    uint32_t        n_features, n_locations;
+} mcb200_shard_run;
+/* origin: per-read aggregation, window-range sums and top candidates over the
+ * returned runs (same reduction as mcb200_query_part_device, rank sequence)       */
+int mcb200_shard_reduce_device (mcb200_workspace* ws, uint32_t part, uint32_t n_shards,
+                                const uint32_t* d_pos, const mcb200_shard_run* runs,
+                                const uint32_t* d_max_win, uint32_t n_queries,
+                                mcb200_candidate* d_top, void* stream);
+
 /* classify() on the device for n_queries candidate lists (d_top as produced by
  * the query entry points): LCA over the ranked lineages of the candidates whose
  * hits exceed (hits0 - hits_min) * hits_diff_fraction; lowest_rank = the rank

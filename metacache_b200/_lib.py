@@ -40,6 +40,12 @@ class Classification(C.Structure):
     _fields_ = [("taxon", C.c_uint32), ("rank", C.c_uint32)]
 
 
+class ShardRun(C.Structure):
+    """mcb200_shard_run: what one owner shard returned for this rank's features"""
+    _fields_ = [("locations", C.c_void_p), ("offsets", C.c_void_p), ("n_features", C.c_uint32),
+                ("n_locations", C.c_uint32)]
+
+
 class DevQueries(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("seq_offsets", C.c_void_p), ("seq_query", C.c_void_p),
                 ("max_win", C.c_void_p), ("n_seqs", C.c_uint32), ("n_queries", C.c_uint32),
@@ -124,6 +130,14 @@ _SIGS = {
     "mcb200_query_sketches_device": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_merge_candidates_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mcb200_query_device": (C.c_int, [_P, C.POINTER(DevQueries), C.POINTER(Sketching), _P, _P]),
+    "mcb200_db_shard_begin": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mcb200_db_shard_maxima": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mcb200_db_shard_finish": (C.c_int, [_P, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32]),
+    "mcb200_db_location_bytes": (C.c_uint32, [_P, C.c_uint32]),
+    "mcb200_shard_route_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "mcb200_shard_probe_device": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, _P, _P]),
+    "mcb200_shard_gather_device": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, _P, _P]),
+    "mcb200_shard_reduce_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.POINTER(ShardRun), _P, C.c_uint32, _P, _P]),
     "mcb200_pack_bases": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P]),
     "mcb200_sketch_packed_device": (C.c_int, [_P, C.POINTER(DevQueries), _P, _P, C.POINTER(Sketching), _P]),
     "mcb200_query_packed_device": (C.c_int, [_P, C.POINTER(DevQueries), _P, _P, C.POINTER(Sketching), _P, _P]),

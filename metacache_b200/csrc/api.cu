@@ -81,6 +81,21 @@ struct Part {
     uint64_t  nkeys = 0, nvalues = 0;        // declared
     uint64_t  keys_loaded = 0, values_loaded = 0;
     bool      begun = false, finished = false;
+    bool      merged = false;                // buckets of several source parts merged (sizes may exceed 254)
+    // feature-space sharding (mcb200_db_shard_begin .. finish): the loaders below collect the
+    // batches' keys owned by this shard instead of inserting them
+    bool      shard_mode = false;
+    uint32_t  shard = 0, n_shards = 1;
+    std::vector<BuiltPart> shard_chunks;
+    uint32_t  max_tgt = 0, max_win = 0;      // hints for a database-wide location packing
+    // The reference merges per-part candidate lists in PART order (candidate_generation.hpp:172-231 applied
+    // part after part, docs/partitioning.md:116-142): on equal hits a target of an earlier part wins whatever
+    // its id.  A merged table reproduces that by numbering targets part-major internally: part_of[tgt] is
+    // learnt from the locations of every source part, tgt_orig translates candidates back (null = identity).
+    uint8_t*  d_part_of = nullptr;
+    uint32_t  n_targets = 0;
+    int       src_part = -1;
+    uint32_t* d_tgt_orig = nullptr;
 };
 
 struct mcb200_db {
@@ -147,10 +162,17 @@ extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
     return db;
 }
 
+static void free_chunks (Part& p) {
+    for (auto& c : p.shard_chunks) { if (c.keys) cudaFree(c.keys); if (c.sizes) cudaFree(c.sizes); if (c.values) cudaFree(c.values); }
+    p.shard_chunks.clear();
+}
 static void free_part (Part& p) {
     if (p.buckets) cudaFree(p.buckets);
     if (p.values) cudaFree(p.values);
     if (p.packed) cudaFree(p.packed);
+    if (p.d_part_of) cudaFree(p.d_part_of);
+    if (p.d_tgt_orig) cudaFree(p.d_tgt_orig);
+    free_chunks(p);
     p = Part{};
 }
 
@@ -172,9 +194,17 @@ extern "C" void mcb200_db_close (mcb200_db* db) {
     if ((part) >= (db)->parts.size()) return fail(MCB200_EINVAL, "part %u out of range (%zu parts)", unsigned(part), (db)->parts.size()); \
     CU(cudaSetDevice((db)->device));
 
+static int part_begin_impl (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues, float max_load_factor);
+
 extern "C" int mcb200_db_part_begin (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues,
                                      float max_load_factor) {
     CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (p.shard_mode) { p.begun = true; ++p.src_part; return 0; }   // next source part of a sharded load
+    return part_begin_impl(db, part, nkeys, nvalues, max_load_factor);
+}
+
+static int part_begin_impl (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues, float max_load_factor) {
     Part& p = db->parts[part];
     free_part(p);
     float lf = max_load_factor;
@@ -209,12 +239,61 @@ static int append_common (mcb200_db* db, Part& p, const uint32_t* d_keys, const 
     return 0;
 }
 
+// sharded load: keep this shard's keys of a batch (device arrays)
+__global__ void mark_parts_kernel (const uint64_t* __restrict__ values, uint64_t n, uint8_t* __restrict__ part_of,
+                                   uint32_t n_targets, uint8_t part, int* __restrict__ error) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t tgt = uint32_t(values[i] >> 32);
+    if (tgt >= n_targets) { atomicExch(error, 5); return; }
+    if (part_of[tgt] != part) part_of[tgt] = part;
+}
+__global__ void renumber_targets_kernel (uint64_t* __restrict__ values, uint64_t n, const uint32_t* __restrict__ new_of_old) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t v = values[i];
+    values[i] = (uint64_t(new_of_old[uint32_t(v >> 32)]) << 32) | uint32_t(v);
+}
+__global__ void translate_targets_kernel (mcb200_candidate* __restrict__ top, uint64_t n, const uint32_t* __restrict__ orig,
+                                          uint32_t n_targets) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = top[i].tgt;
+    if (t < n_targets) top[i].tgt = orig[t];
+}
+
+static int shard_collect (mcb200_db* db, Part& p, const uint32_t* d_keys, const uint8_t* d_sizes,
+                          const uint64_t* d_values, uint64_t nkeys, uint64_t nvalues) {
+    if (p.d_part_of && nvalues) {
+        mark_parts_kernel<<<unsigned((nvalues + 255) / 256), 256, 0, db->stream>>>(
+            d_values, nvalues, p.d_part_of, p.n_targets, uint8_t(std::max(p.src_part, 0)), db->d_error);
+        count_launch();
+    }
+    BuiltPart c{};
+    const int rc = shard_filter(d_keys, d_sizes, d_values, nkeys, p.shard, p.n_shards, c, db->stream);
+    if (rc) return fail(rc == -2 ? MCB200_EINVAL : MCB200_ECUDA, "sharded load: filtering a batch failed: %s",
+                        rc == -2 ? "batch too large" : cudaGetErrorString(cudaGetLastError()));
+    if (c.nkeys) p.shard_chunks.push_back(c);
+    return 0;
+}
+
 extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,
                                       const uint8_t* sizes, const uint64_t* values,
                                       uint64_t nkeys, uint64_t nvalues) {
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
+    if (p.shard_mode) {
+        if (nkeys == 0) return 0;
+        DevBuf<uint64_t> vals;
+        CU(db->st_keys.ensure(nkeys)); CU(db->st_sizes.ensure(nkeys)); CU(vals.ensure(nvalues));
+        CU(cudaMemcpyAsync(db->st_keys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, db->stream));
+        CU(cudaMemcpyAsync(db->st_sizes.p, sizes, nkeys, cudaMemcpyHostToDevice, db->stream));
+        CU(cudaMemcpyAsync(vals.p, values, nvalues * 8, cudaMemcpyHostToDevice, db->stream));
+        const int rc = shard_collect(db, p, db->st_keys.p, db->st_sizes.p, vals.p, nkeys, nvalues);
+        vals.release();
+        return rc;
+    }
     if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
         return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
     if (nkeys == 0) return 0;
@@ -234,6 +313,7 @@ extern "C" int mcb200_db_part_append_device (mcb200_db* db, uint32_t part, const
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
+    if (p.shard_mode) return nkeys ? shard_collect(db, p, d_keys, d_sizes, d_values, nkeys, nvalues) : 0;
     if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
         return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
     if (nkeys == 0) return 0;
@@ -248,6 +328,7 @@ extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun) return fail(MCB200_ESTATE, "part %u: finish without begin", part);
+    if (p.shard_mode) { p.begun = false; return 0; }         // the table is built by mcb200_db_shard_finish
     int err = 0;
     CU(cudaMemcpyAsync(&err, db->d_error, sizeof(int), cudaMemcpyDeviceToHost, db->stream));
     CU(cudaStreamSynchronize(db->stream));
@@ -258,10 +339,136 @@ extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
                     (unsigned long long)p.keys_loaded, (unsigned long long)p.nkeys,
                     (unsigned long long)p.values_loaded, (unsigned long long)p.nvalues);
     if (table_finalize(p.buckets, p.nbuckets, p.values, p.values_loaded, p.packed, p.packed_bytes, p.win_bits,
-                       db->stream) != 0)
+                       db->stream, p.max_tgt, p.max_win) != 0)
         return fail(MCB200_ECUDA, "part %u: layout finalisation failed: %s", part, cudaGetErrorString(cudaGetLastError()));
     cudaFree(p.values); p.values = nullptr;
     p.finished = true;
+    return 0;
+}
+
+extern "C" int mcb200_db_shard_begin (mcb200_db* db, uint32_t part, uint32_t shard, uint32_t n_shards,
+                                      uint32_t n_targets) {
+    CHECK_DB(db, part);
+    if (n_shards == 0 || n_shards > 32 || shard >= n_shards) return fail(MCB200_EINVAL, "shard %u of %u unsupported (1..32 shards)", shard, n_shards);
+    Part& p = db->parts[part];
+    free_part(p);
+    p.shard_mode = true; p.shard = shard; p.n_shards = n_shards;
+    if (n_targets) {
+        CU(cudaMalloc(&p.d_part_of, n_targets));
+        CU(cudaMemsetAsync(p.d_part_of, 0xFF, n_targets, db->stream));
+        CU(cudaMemsetAsync(db->d_error, 0, sizeof(int), db->stream));
+        p.n_targets = n_targets;
+    }
+    return 0;
+}
+
+extern "C" int mcb200_db_shard_finish (mcb200_db* db, uint32_t part, float max_load_factor,
+                                       uint32_t max_target_id, uint32_t max_window_id) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.shard_mode) return fail(MCB200_ESTATE, "part %u: mcb200_db_shard_begin must be called first", part);
+    if (p.begun) return fail(MCB200_ESTATE, "part %u: a source part is still open (finish it first)", part);
+    cudaStream_t st = db->stream;
+    uint64_t nrec = 0, nval = 0;
+    for (auto& c : p.shard_chunks) { nrec += c.nkeys; nval += c.nvalues; }
+    // concatenate the collected batches (arrival order = part order)
+    uint32_t* keys = nullptr; uint8_t* sizes = nullptr; uint64_t* values = nullptr;
+    cudaError_t e = cudaMalloc(&keys, std::max<uint64_t>(nrec, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sizes, std::max<uint64_t>(nrec, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&values, std::max<uint64_t>(nval, 1) * 8);
+    uint64_t ko = 0, vo = 0;
+    for (auto& c : p.shard_chunks) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(keys + ko, c.keys, c.nkeys * 4, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sizes + ko, c.sizes, c.nkeys, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess && c.nvalues) e = cudaMemcpyAsync(values + vo, c.values, c.nvalues * 8, cudaMemcpyDeviceToDevice, st);
+        ko += c.nkeys; vo += c.nvalues;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    free_chunks(p);
+    if (e != cudaSuccess) {
+        if (keys) cudaFree(keys); if (sizes) cudaFree(sizes); if (values) cudaFree(values);
+        return fail(MCB200_ECUDA, "sharded load: concatenation failed: %s", cudaGetErrorString(e));
+    }
+    // part-major target numbering (see Part::d_part_of)
+    uint32_t* d_tgt_orig = nullptr;
+    const uint32_t n_targets = p.n_targets;
+    if (p.d_part_of) {
+        int err = 0;
+        std::vector<uint8_t> part_of(n_targets);
+        e = cudaMemcpy(&err, db->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(part_of.data(), p.d_part_of, n_targets, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess || err == 5) {
+            cudaFree(keys); cudaFree(sizes); cudaFree(values);
+            if (e != cudaSuccess) return fail(MCB200_ECUDA, "sharded load: %s", cudaGetErrorString(e));
+            return fail(MCB200_EINVAL, "part %u: a location names a target id >= the %u targets declared", part, n_targets);
+        }
+        std::vector<uint32_t> order(n_targets), new_of_old(n_targets);
+        for (uint32_t t = 0; t < n_targets; ++t) order[t] = t;
+        std::stable_sort(order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return part_of[a] < part_of[b]; });
+        bool identity = true;
+        for (uint32_t i = 0; i < n_targets; ++i) { new_of_old[order[i]] = i; identity &= (order[i] == i); }
+        if (!identity && nval) {
+            uint32_t* d_new = nullptr;
+            e = cudaMalloc(&d_new, uint64_t(n_targets) * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&d_tgt_orig, uint64_t(n_targets) * 4);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_new, new_of_old.data(), uint64_t(n_targets) * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_tgt_orig, order.data(), uint64_t(n_targets) * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                renumber_targets_kernel<<<unsigned((nval + 255) / 256), 256, 0, st>>>(values, nval, d_new);
+                count_launch();
+                e = cudaStreamSynchronize(st);
+            }
+            if (d_new) cudaFree(d_new);
+            if (e != cudaSuccess) {
+                cudaFree(keys); cudaFree(sizes); cudaFree(values); if (d_tgt_orig) cudaFree(d_tgt_orig);
+                return fail(MCB200_ECUDA, "sharded load: renumbering targets failed: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    CU(cudaMemsetAsync(db->d_error, 0, sizeof(int), st));
+    MergedPart m;
+    int rc = shard_merge(keys, sizes, values, nrec, nval, m, db->d_error, st);       // consumes the three arrays
+    if (rc) return fail(rc == -2 ? MCB200_EINVAL : MCB200_ECUDA, "sharded load: merging buckets failed: %s",
+                        rc == -2 ? "too many keys for one shard" : cudaGetErrorString(cudaGetLastError()));
+    {
+        int err = 0;
+        e = cudaMemcpy(&err, db->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess || err == 4) {
+            if (m.keys) cudaFree(m.keys); if (m.sizes) cudaFree(m.sizes); if (m.offsets) cudaFree(m.offsets); if (m.values) cudaFree(m.values);
+            if (e != cudaSuccess) return fail(MCB200_ECUDA, "sharded load: %s", cudaGetErrorString(e));
+            return fail(MCB200_EINVAL, "part %u: a merged bucket exceeds %u locations", part, kSizeMask);
+        }
+    }
+    const uint32_t shard = p.shard, n_shards = p.n_shards;
+    rc = part_begin_impl(db, part, m.nkeys, m.nvalues, max_load_factor);               // resets the part
+    Part& q = db->parts[part];
+    q.shard = shard; q.n_shards = n_shards; q.merged = true;
+    q.max_tgt = max_target_id; q.max_win = max_window_id;
+    q.d_tgt_orig = d_tgt_orig; q.n_targets = n_targets;
+    if (!rc && m.nkeys) {
+        e = cudaMemcpyAsync(q.values, m.values, m.nvalues * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) {
+            launch_table_insert_wide(q.buckets, q.nbuckets, m.keys, m.sizes, m.offsets, q.values, m.nkeys, db->d_error, st);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(MCB200_ECUDA, "sharded load: table insertion failed: %s", cudaGetErrorString(e));
+        q.keys_loaded = m.nkeys; q.values_loaded = m.nvalues;
+    }
+    if (m.keys) cudaFree(m.keys); if (m.sizes) cudaFree(m.sizes); if (m.offsets) cudaFree(m.offsets); if (m.values) cudaFree(m.values);
+    if (rc) return rc;
+    return mcb200_db_part_finish(db, part);
+}
+
+extern "C" int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* max_target_id, uint32_t* max_window_id) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.shard_mode || !max_target_id || !max_window_id) return fail(MCB200_ESTATE, "part %u: not collecting a shard", part);
+    uint32_t m[2] = {0, 0};
+    for (auto& c : p.shard_chunks)
+        if (device_loc_max(c.values, c.nvalues, m, db->stream) != 0)
+            return fail(MCB200_ECUDA, "sharded load: scanning the locations failed: %s", cudaGetErrorString(cudaGetLastError()));
+    *max_target_id = m[0]; *max_window_id = m[1];
     return 0;
 }
 
@@ -335,6 +542,7 @@ extern "C" int mcb200_db_part_export (const mcb200_db* db, uint32_t part, uint32
     CHECK_DB(db, part);
     const Part& p = db->parts[part];
     if (!p.finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (p.merged) return fail(MCB200_EINVAL, "part %u holds merged buckets of several parts: not expressible in the .cache format", part);
     if (table_export(p.buckets, p.nbuckets, p.packed, p.win_bits, p.keys_loaded, p.values_loaded, keys, sizes,
                      values, db->stream) != 0)
         return fail(MCB200_ECUDA, "export failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -357,6 +565,7 @@ struct mcb200_workspace {
     DevBuf<uint64_t> scratch;            // 12 B per entry: keys then cnt
     uint64_t scratch_entries = 0;
     DevBuf<int> error;
+    DevBuf<ListArgs> lists;              // device copy of the runs handed to mcb200_shard_reduce_device
     DevBuf<mcb200_candidate> part_tops;
     DevBuf<uint64_t> hit_counts, hit_offsets, allhits;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
@@ -445,7 +654,7 @@ extern "C" void mcb200_workspace_destroy (mcb200_workspace* ws) {
     ws->codes.release(); ws->amb.release(); ws->seq_nwin.release(); ws->seq_win_off.release();
     ws->win_seq.release(); ws->qry_win_off.release(); ws->feats.release(); ws->heavy_list.release();
     ws->heavy_count.release(); ws->counters.release(); ws->scratch_cursor.release();
-    ws->scratch.release(); ws->error.release(); ws->part_tops.release(); ws->hit_counts.release();
+    ws->scratch.release(); ws->error.release(); ws->part_tops.release(); ws->lists.release(); ws->hit_counts.release();
     ws->hit_offsets.release(); ws->allhits.release();
     if (ws->scan_tmp) cudaFree(ws->scan_tmp);
     for (auto& es : ws->ev_sets) {
@@ -602,6 +811,7 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
     a.scratch = ws->scratch.p; a.scratch_entries = ws->scratch_entries;
     a.scratch_cursor = ws->scratch_cursor.p;
     a.counters = ws->profiling ? ws->counters.p : nullptr; a.error = ws->error.p;
+    a.lists = nullptr;
     return a;
 }
 
@@ -667,6 +877,101 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
     if (prof) CU(cudaEventRecord(ws->ev->q[part * 3 + 1], st));
     launch_query_heavy(a, ws->db->sm_count, st);
     if (prof) { CU(cudaEventRecord(ws->ev->q[part * 3 + 2], st)); ws->ev->part_done[part] = 1; }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// feature-space sharding: the three device steps around the two exchanges (kernels_shard.cu)
+// ---------------------------------------------------------------------------
+extern "C" uint32_t mcb200_db_location_bytes (const mcb200_db* db, uint32_t part) {
+    if (!db || part >= db->parts.size() || !db->parts[part].finished) return 0;
+    return db->parts[part].win_bits ? 4u : 8u;
+}
+
+extern "C" int mcb200_shard_route_device (mcb200_workspace* ws, const uint32_t* d_feats,
+                                          const uint32_t* d_qry_win_off, uint32_t n_queries, uint32_t sketchlen,
+                                          uint32_t n_shards, uint32_t* d_pos, uint32_t* d_send_feats, void* stream) {
+    if (!ws || !d_feats || !d_qry_win_off || !d_pos || !d_send_feats) return fail(MCB200_EINVAL, "null argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(MCB200_EINVAL, "%u shards unsupported (1..%u)", n_shards, kMaxShards);
+    if (sketchlen < 1 || sketchlen > 32) return fail(MCB200_EINVAL, "sketchlen %u unsupported (1..32)", sketchlen);
+    if (uint64_t(n_shards) * (uint64_t(n_queries) + 1) + 1 >= (1ull << 31)) return fail(MCB200_EINVAL, "batch too large for one routing call");
+    CU(cudaSetDevice(ws->db->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    launch_shard_route(d_feats, d_qry_win_off, n_queries, sketchlen, n_shards, d_pos, d_send_feats,
+                       ws->scan_tmp, ws->scan_tmp_bytes, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcb200_shard_probe_device (mcb200_workspace* ws, uint32_t part, const uint32_t* d_feats, uint64_t n,
+                                          uint32_t* d_off, uint64_t* d_data, void* stream) {
+    if (!ws || !d_off || (n && (!d_feats || !d_data))) return fail(MCB200_EINVAL, "null argument");
+    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (n >= (1ull << 32) - 2) return fail(MCB200_EINVAL, "too many features for one call");
+    CU(cudaSetDevice(ws->db->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    const Part& p = ws->db->parts[part];
+    launch_shard_probe(TableView{p.buckets, p.nbuckets, p.packed, p.win_bits}, d_feats, n, d_off, d_data,
+                       ws->scan_tmp, ws->scan_tmp_bytes, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcb200_shard_gather_device (mcb200_workspace* ws, uint32_t part, const uint32_t* d_off,
+                                           const uint64_t* d_data, uint64_t n, void* d_locs, void* stream) {
+    if (!ws || (n && (!d_off || !d_data || !d_locs))) return fail(MCB200_EINVAL, "null argument");
+    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
+    CU(cudaSetDevice(ws->db->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    const Part& p = ws->db->parts[part];
+    launch_shard_gather(TableView{p.buckets, p.nbuckets, p.packed, p.win_bits}, d_off, d_data, n, d_locs, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcb200_shard_reduce_device (mcb200_workspace* ws, uint32_t part, uint32_t n_shards,
+                                           const uint32_t* d_pos, const mcb200_shard_run* runs,
+                                           const uint32_t* d_max_win, uint32_t n_queries,
+                                           mcb200_candidate* d_top, void* stream) {
+    if (!ws || !d_pos || !runs || !d_max_win || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(MCB200_EINVAL, "%u shards unsupported (1..%u)", n_shards, kMaxShards);
+    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (n_queries > ws->max_queries) return fail(MCB200_EINVAL, "batch exceeds workspace capacity");
+    if (ws->db->d_tax) return fail(MCB200_EINVAL, "feature-sharded queries generate candidates at rank sequence only");
+    CU(cudaSetDevice(ws->db->device));
+    if (n_queries == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ws->last_stream = st;
+    { int rc = ensure_default_scratch(ws); if (rc) return rc; }
+    ListArgs la{};
+    la.n_src = n_shards; la.nq = n_queries; la.pos = d_pos;
+    for (uint32_t o = 0; o < n_shards; ++o) {
+        if (runs[o].n_features && (!runs[o].offsets || (runs[o].n_locations && !runs[o].locations)))
+            return fail(MCB200_EINVAL, "run %u: null buffer", o);
+        la.src[o] = ListSource{runs[o].locations, runs[o].offsets, runs[o].n_features, runs[o].n_locations};
+    }
+    CU(ws->lists.ensure(1));
+    CU(cudaMemcpyAsync(ws->lists.p, &la, sizeof la, cudaMemcpyHostToDevice, st));
+    mcb200_dev_queries q{}; q.max_win = d_max_win; q.n_queries = n_queries;
+    const mcb200_dev_queries saved_q = ws->q;
+    ws->q = q;
+    QueryArgs a = make_args(ws, part, d_top);
+    ws->q = saved_q;
+    a.feats = nullptr; a.qry_win_off = nullptr; a.tax_of_tgt = nullptr; a.n_tax = 0;
+    a.lists = ws->lists.p;
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
+    CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
+    launch_query_lists(a, ws->warp_cap, ws->db->sm_count, st);
+    const Part& p = ws->db->parts[part];
+    if (p.d_tgt_orig) {
+        const uint64_t n = uint64_t(n_queries) * ws->maxc;
+        translate_targets_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(d_top, n, p.d_tgt_orig, p.n_targets);
+        count_launch();
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1101,15 +1406,19 @@ extern "C" int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const
     int64_t added = 0;
     const uint64_t pos = s.n_bases;
     const uint64_t first = offsets[0];
-    uint64_t last = first;
+    uint64_t last = first, rule_len = ~0ull;
+    uint32_t mw = 0;
     for (uint32_t i = 0; i < n_queries; ++i) {
         const uint64_t o0 = offsets[paired ? 2 * uint64_t(i) : i];
         const uint64_t o1 = offsets[(paired ? 2 * uint64_t(i) : i) + 1];
         const uint64_t o2 = paired ? offsets[2 * uint64_t(i) + 2] : o1;
         if (o0 != last || o1 < o0 || o2 < o1) return fail(MCB200_EINVAL, "offsets must ascend without gaps");
         const uint64_t l1 = o1 - o0, l2 = o2 - o1;
-        // make_candidate_generation_rules (candidate_structs.hpp:134-151)
-        const uint32_t mw = uint32_t(2 + std::max<uint64_t>(l1 + l2, insert_size_max) / winstride);
+        // make_candidate_generation_rules (candidate_structs.hpp:134-151); reads of one length share it
+        if (l1 + l2 != rule_len) {
+            rule_len = l1 + l2;
+            mw = uint32_t(2 + std::max<uint64_t>(rule_len, insert_size_max) / winstride);
+        }
         // a read with an empty first mate keeps its (non-empty) second mate as only sequence
         const bool ok = (l1 == 0 && l2 > 0) ? slot_add_meta(b, s, l2, 0, mw) : slot_add_meta(b, s, l1, l2, mw);
         if (!ok) break;

@@ -46,15 +46,25 @@ __host__ __device__ __forceinline__ uint64_t bucket_of (uint32_t key, uint64_t n
     return (uint64_t(mix32(key)) * nbuckets) >> 32;
 }
 
+// ---- feature-space sharding (one shard per GPU) -------------------------------
+// Owner of a feature among n_shards.  Features are min-hash values (small numbers), and the table's
+// bucket index uses mix32: the owner is derived from a DIFFERENT mixing function so that the keys of
+// one shard still spread over the whole table of that shard.
+__host__ __device__ __forceinline__ uint32_t shard_of (uint32_t key, uint32_t n_shards) {
+    return uint32_t((uint64_t(hash32(key ^ 0x9E3779B9u)) * n_shards) >> 32);
+}
+
 // ---- 16-byte table slot -----------------------------------------------------
 //   key   : feature
-//   meta  : bucket size in bits 0..7 (0 = empty slot, 1..254 = locations)
+//   meta  : bucket size in bits 0..15 (0 = empty slot; 1..254 for a part as the reference
+//           stores it, up to 65535 when the buckets of several parts are merged, see table.cu)
 //   data  : 64-bit locations: size == 1 -> the location itself (inline)
 //           32-bit packed locations: size <= 2 -> the locations themselves
 //           else index (in elements) of the bucket's first location in `values`,
 //           which starts on a 64-byte boundary (one memory request per line)
 // Two slots share one 32-byte DRAM sector ("bucket"); a lookup reads whole
 // sectors with one 256-bit load.
+constexpr uint32_t kSizeMask = 0xFFFFu;
 struct __align__(16) Slot {
     uint32_t key;
     uint32_t meta;
@@ -105,9 +115,9 @@ __device__ __forceinline__ uint32_t table_find (const TableView& t, uint32_t key
         Slot s0, s1;
         load_bucket(t.buckets + b, s0, s1);
         ++sectors_read;
-        if (s0.meta != 0 && s0.key == key) { data = s0.data; return s0.meta & 0xFFu; }
+        if (s0.meta != 0 && s0.key == key) { data = s0.data; return s0.meta & kSizeMask; }
         if (s0.meta == 0) return 0;
-        if (s1.meta != 0 && s1.key == key) { data = s1.data; return s1.meta & 0xFFu; }
+        if (s1.meta != 0 && s1.key == key) { data = s1.data; return s1.meta & kSizeMask; }
         if (s1.meta == 0) return 0;
         if (++b == t.nbuckets) b = 0;
     }

@@ -44,6 +44,9 @@ void launch_sketch (const uint32_t* codes, const uint32_t* amb, const uint32_t* 
 void launch_table_insert (Bucket* buckets, uint64_t nbuckets, const uint32_t* keys,
                           const uint8_t* sizes, const uint64_t* offsets, const uint64_t* values,
                           uint64_t nkeys, int* d_error, cudaStream_t st);
+void launch_table_insert_wide (Bucket* buckets, uint64_t nbuckets, const uint32_t* keys,
+                               const uint32_t* sizes, const uint64_t* offsets, const uint64_t* values,
+                               uint64_t nkeys, int* d_error, cudaStream_t st);
 // exclusive scan of u8 sizes -> u64 offsets (+base), device
 void device_scan_sizes (const uint8_t* sizes, uint64_t n, uint64_t base, uint64_t* offsets,
                         void*& tmp, size_t& tmp_bytes, cudaStream_t st);
@@ -57,14 +60,41 @@ int  table_export (const Bucket* buckets, uint64_t nbuckets, const void* values,
                    uint64_t* h_values, cudaStream_t st);
 // after all batches are inserted: pack + align the locations, rewrite the slots' data words
 int  table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_values, uint64_t nvalues,
-                     void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st);
+                     void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st,
+                     uint32_t at_least_tgt = 0, uint32_t at_least_win = 0);
 // build from (feature, location) pairs produced by sketching targets
 struct BuiltPart { uint32_t* keys; uint8_t* sizes; uint64_t* values; uint64_t nkeys, nvalues; };
 int  build_from_sketches (const uint32_t* feats, const uint32_t* win_seq, const uint32_t* seq_win_off,
                           uint64_t nwin, uint32_t s, uint32_t first_target, uint32_t max_locations,
                           BuiltPart& out, cudaStream_t st);
 
+// feature-space sharding at load time: keep the keys of a batch owned by `shard` (device arrays in,
+// freshly allocated device arrays out), and merge the buckets of equal keys of the concatenated batches
+int  shard_filter (const uint32_t* keys, const uint8_t* sizes, const uint64_t* values, uint64_t nkeys,
+                   uint32_t shard, uint32_t n_shards, BuiltPart& out, cudaStream_t st);
+int  device_loc_max (const uint64_t* values, uint64_t n, uint32_t out[2], cudaStream_t st);
+struct MergedPart { uint32_t* keys = nullptr; uint32_t* sizes = nullptr; uint64_t* offsets = nullptr;
+                    uint64_t* values = nullptr; uint64_t nkeys = 0, nvalues = 0; };
+int  shard_merge (uint32_t* keys, uint8_t* sizes, uint64_t* values, uint64_t nrec, uint64_t nvalues,
+                  MergedPart& out, int* d_error, cudaStream_t st);
+
 // ---- kernels_query.cu -------------------------------------------------------
+// Feature-space sharding, origin side: the locations of a read arrive as one contiguous run per
+// owner shard (kernels_shard.cu) instead of being fetched from the local table.
+constexpr uint32_t kMaxShards = 32;
+struct ListSource {
+    const void*     locs;     // locations returned by this owner for my reads (u32 packed or u64), read-major
+    const uint32_t* off;      // [nfeat] offset of every feature's list in the OWNER's numbering (off[0] = base)
+    uint32_t        nfeat;    // features I sent to this owner
+    uint32_t        nlocs;    // locations returned by this owner
+};
+struct ListArgs {
+    uint32_t        n_src;
+    uint32_t        nq;       // reads of this batch
+    const uint32_t* pos;      // [n_src][nq + 1] exclusive scan of the per-(owner, read) feature counts
+    ListSource      src[kMaxShards];
+};
+
 struct QueryArgs {
     const uint32_t* feats;        // [nwin][s]
     const uint32_t* qry_win_off;  // [nq+1]
@@ -86,9 +116,25 @@ struct QueryArgs {
     unsigned long long* scratch_cursor;
     unsigned long long* counters; // [8] see mcb200_workspace_counters
     int*            error;        // sticky device error flag
+    const ListArgs* lists;        // device copy; only read by the *_lists launches
 };
 void launch_query_warp  (const QueryArgs& a, uint32_t cap, int sm_count, cudaStream_t st);
 void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st);
+// same reductions over location lists received from the owner shards (a.lists) instead of the table
+void launch_query_lists (const QueryArgs& a, uint32_t cap, int sm_count, cudaStream_t st);
+
+// ---- kernels_shard.cu -------------------------------------------------------
+// origin: per-(owner, read) feature counts -> exclusive scan `pos` ([n_shards][nq + 1] + 1 total) ->
+// features grouped by owner, reads in order (send buffer)
+void launch_shard_route (const uint32_t* feats, const uint32_t* qry_win_off, uint32_t nq, uint32_t s,
+                         uint32_t n_shards, uint32_t* pos, uint32_t* send_feats, void*& tmp, size_t& tmp_bytes,
+                         cudaStream_t st);
+// owner: slot lookup of n features -> exclusive scan of the bucket sizes off[n + 1], slot data words
+void launch_shard_probe (const TableView& t, const uint32_t* feats, uint64_t n, uint32_t* off, uint64_t* data,
+                         void*& tmp, size_t& tmp_bytes, cudaStream_t st);
+// owner: bucket contents -> locs[off[i] .. off[i + 1]) (u32 packed when t.win_bits, else u64)
+void launch_shard_gather (const TableView& t, const uint32_t* off, const uint64_t* data, uint64_t n, void* locs,
+                          cudaStream_t st);
 // counts locations per query (for all-hits offsets)
 void launch_count_hits (const QueryArgs& a, uint64_t* counts, cudaStream_t st);
 void launch_merge_candidates (const mcb200_candidate* parts, uint32_t n_lists, uint32_t nq,

@@ -297,7 +297,9 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
 
 // in_queue < 0: all reads of the batch; else the reads of that overflow queue (a second pass with a
 // larger table).  Reads this pass cannot settle go to out_queue.
-template <class K>
+// kLists: the read's locations come as one run per owner shard (a.lists, feature-space sharding,
+// kernels_shard.cu) instead of from the local table; everything after the aggregation is the same.
+template <class K, bool kLists>
 __global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
@@ -338,9 +340,13 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     uint32_t* out_count = a.heavy_count + 2 * out_queue;
     for (uint32_t qi = blockIdx.x * kQWarps + warp; qi < n_in; qi += nwarps) {
     const uint32_t q = in_list ? in_list[qi] : qi;
-    const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
-    const uint32_t nslots = (w1 - w0) * a.s;
-    const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+    uint32_t nslots = 0;
+    const uint32_t* fbase = nullptr;
+    if (!kLists) {
+        const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
+        nslots = (w1 - w0) * a.s;
+        fbase = a.feats + uint64_t(w0) * a.s;
+    }
     const uint32_t W = __ldg(a.max_win + q);
     mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
     uint32_t sectors = 0, nfeat = 0, H = 0, D = 0, list_lines = 0;
@@ -353,6 +359,47 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 
     // ---- probe + aggregate -------------------------------------------------
     bool ok = true;
+    if (kLists) {
+        // lane o: the run of this read's locations returned by owner o
+        const ListArgs& la = *a.lists;
+        uint32_t b = 0, n = 0;
+        if (lane < la.n_src) {
+            const ListSource& src = la.src[lane];
+            const uint32_t* pp = la.pos + uint64_t(lane) * (la.nq + 1);
+            const uint32_t seg = __ldg(pp), i0 = __ldg(pp + q) - seg, i1 = __ldg(pp + q + 1) - seg;
+            if (i1 > i0) {
+                const uint32_t base = __ldg(src.off);
+                b = __ldg(src.off + i0) - base;
+                n = ((i1 >= src.nfeat) ? src.nlocs : __ldg(src.off + i1) - base) - b;
+            }
+        }
+        const uint32_t incl = warp_incl_scan(n);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        H = total;
+        sbase[lane] = incl - n;
+        ssec[lane] = b;
+        if (lane == 31) sbase[32] = total;
+        __syncwarp();
+        for (uint32_t p0 = 0; p0 < total && ok; p0 += 128) {
+            K v[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = p0 + u * 32 + lane;
+                v[u] = AK::kEmpty;
+                if (p < total) {
+                    uint32_t o = 0;
+                    #pragma unroll
+                    for (uint32_t step = 16; step > 0; step >>= 1)
+                        if (sbase[o + step] <= p) o += step;
+                    v[u] = __ldg(static_cast<const K*>(la.src[o].locs) + ssec[o] + (p - sbase[o]));
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok) ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, v[u] != AK::kEmpty, v[u], D);
+        }
+        __syncwarp();
+    }
     for (uint32_t c = 0; c < nslots && ok; c += 32) {
         const uint32_t idx = c + lane;
         const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
@@ -730,18 +777,20 @@ query_warp_kernel (QueryArgs a, uint32_t T)
     warp_stats(a, fused, H, nfeat, sectors);
 }
 
-void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st)
+static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st, bool lists)
 {
     if (!a.nq) return;
     static std::atomic<uint64_t> attr_devices{0};
     if (first_use_on_device(attr_devices)) {
         cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(query_fast_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(query_fast_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     const unsigned grid = (a.nq + kQWarps - 1) / kQWarps;
-    if (!a.tax_of_tgt && !a.allhits) {
+    if (lists || (!a.tax_of_tgt && !a.allhits)) {
         // top hits only at rank "sequence": the sort-free kernel
         // pass 0: every read, small per-warp tables, full occupancy; pass 1: the reads that overflowed them
         // (queue 0), 1024-slot tables, 1-2 CTAs per SM; what is left (queue 1) goes to the CTA kernel
@@ -750,14 +799,18 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream
             const uint32_t Tp = pass == 0 ? T : std::max<uint32_t>(T, kSecondPassSlots);
             const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
             int per_sm = 0;
-            if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t>, kQWarps * 32, smem);
-            else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t>, kQWarps * 32, smem);
+            if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false>, kQWarps * 32, smem);
+            else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t, false>, kQWarps * 32, smem);
             if (per_sm < 1) per_sm = 1;
             if (pass == 0 && cap >= 1 && cap < per_sm) per_sm = cap;
             const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
             const int in_queue = pass == 0 ? -1 : 0;
-            if (a.table.win_bits) query_fast_kernel<uint32_t><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
-            else                  query_fast_kernel<uint64_t><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            if (lists) {
+                if (a.table.win_bits) query_fast_kernel<uint32_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+                else                  query_fast_kernel<uint64_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            }
+            else if (a.table.win_bits) query_fast_kernel<uint32_t, false><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            else                       query_fast_kernel<uint64_t, false><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             if (pass == 1) count_launch();
         }
     } else {
@@ -766,6 +819,10 @@ void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream
         else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, T);
     }
     count_launch();
+}
+
+void launch_query_warp (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st) {
+    launch_query_warp_impl(a, T, sm_count, st, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -808,7 +865,7 @@ __device__ void block_bitonic_sort (KeyPtr keys, uint32_t n) {
 // Two tiers share this kernel: tier 0 (small shared-memory lists, many CTAs per SM) takes the reads
 // the warp kernel passed on and forwards those whose list does not fit to the queue of tier 1 (one CTA
 // per SM, 192 KB list, global scratch beyond that).
-template <int kHeavyThreads>
+template <int kHeavyThreads, bool kLists>
 __global__ void __launch_bounds__(kHeavyThreads)
 query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_queue, uint32_t nq_cap)
 {
@@ -838,20 +895,39 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
         const uint32_t q = s_q;
         if (q == 0xFFFFFFFFu) break;
 
-        const uint32_t w0 = a.qry_win_off[q], w1 = a.qry_win_off[q + 1];
-        const uint32_t nslots = (w1 - w0) * a.s;
-        const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+        uint32_t nslots = 0;
+        const uint32_t* fbase = nullptr;
+        if (!kLists) {
+            const uint32_t w0 = a.qry_win_off[q], w1 = a.qry_win_off[q + 1];
+            nslots = (w1 - w0) * a.s;
+            fbase = a.feats + uint64_t(w0) * a.s;
+        }
         mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
         uint32_t sectors = 0, nfeat = 0;
 
         // ---- pass 1: total number of locations -----------------------------
         uint32_t mysum = 0;
+        uint32_t run_begin = 0;
+        if (kLists) {
+            // thread o: the run of this read's locations returned by owner o (as in query_fast_kernel)
+            const ListArgs& la = *a.lists;
+            if (tid < la.n_src) {
+                const ListSource& src = la.src[tid];
+                const uint32_t* pp = la.pos + uint64_t(tid) * (la.nq + 1);
+                const uint32_t seg = pp[0], i0 = pp[q] - seg, i1 = pp[q + 1] - seg;
+                if (i1 > i0) {
+                    const uint32_t base = src.off[0];
+                    run_begin = src.off[i0] - base;
+                    mysum = ((i1 >= src.nfeat) ? src.nlocs : src.off[i1] - base) - run_begin;
+                }
+            }
+        }
         for (uint32_t idx = tid; idx < nslots; idx += kHeavyThreads) {
             const uint32_t f = fbase[idx];
             if (f != kNoFeature) { uint64_t d; mysum += table_find(a.table, f, d, sectors); ++nfeat; }
         }
         uint32_t H = 0;
-        block_excl_scan<kHeavyThreads>(mysum, s_warp, H);
+        const uint32_t run_start = block_excl_scan<kHeavyThreads>(mysum, s_warp, H);
         if (H == 0) { if (tid == 0) write_empty(top, 0, a.maxc); continue; }
         const uint32_t n = max(pow2_ceil(H), 2u);
 
@@ -877,6 +953,26 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
             cnt  = reinterpret_cast<uint32_t*>(a.scratch + a.scratch_entries) + off;
         }
 
+        if (kLists) {
+            // ---- pass 2: copy the runs (unpacked to u64 keys) ------------------
+            const ListArgs& la = *a.lists;
+            if (tid < kMaxShards) {
+                s_base[tid] = (tid < la.n_src) ? run_start : H;
+                s_data[tid] = run_begin;
+            }
+            if (tid == 0) s_base[kMaxShards] = H;
+            __syncthreads();
+            for (uint32_t p = tid; p < H; p += kHeavyThreads) {
+                uint32_t o = 0;
+                #pragma unroll
+                for (uint32_t step = kMaxShards / 2; step > 0; step >>= 1)
+                    if (s_base[o + step] <= p) o += step;
+                const uint64_t at = s_data[o] + (p - s_base[o]);
+                keys[p] = a.table.win_bits ? unpack_loc(static_cast<const uint32_t*>(la.src[o].locs)[at], a.table.win_bits)
+                                           : static_cast<const uint64_t*>(la.src[o].locs)[at];
+            }
+            __syncthreads();
+        }
         // ---- pass 2: gather, 256 feature slots at a time -------------------
         uint32_t filled = 0;
         for (uint32_t c = 0; c < nslots; c += kHeavyThreads) {
@@ -980,17 +1076,34 @@ constexpr uint32_t kHeavySmallEntries = 2048;    // tier 0: 24 KB, up to 8 CTAs 
 constexpr int      kHeavySmall = 256;            // threads per CTA, tier 0
 constexpr int      kHeavyBig   = 1024;           // tier 1: the one CTA of an SM uses all its warp slots
 
-void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st)
+static void launch_query_heavy_impl (const QueryArgs& a, int sm_count, cudaStream_t st, bool lists)
 {
     static std::atomic<uint64_t> attr_devices{0};
     const size_t smem = size_t(kHeavySmemEntries) * 12;
-    if (first_use_on_device(attr_devices))
-        cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (first_use_on_device(attr_devices)) {
+        cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    }
     // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
-    const uint32_t in_queue = (!a.tax_of_tgt && !a.allhits) ? 1u : 0u;
-    query_heavy_kernel<kHeavySmall><<<sm_count * 8, kHeavySmall, size_t(kHeavySmallEntries) * 12, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);
-    query_heavy_kernel<kHeavyBig><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, in_queue + 1, a.nq_cap);
+    const uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
+    const size_t small = size_t(kHeavySmallEntries) * 12;
+    if (lists) {
+        query_heavy_kernel<kHeavySmall, true><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);
+        query_heavy_kernel<kHeavyBig, true><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, in_queue + 1, a.nq_cap);
+    } else {
+        query_heavy_kernel<kHeavySmall, false><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);
+        query_heavy_kernel<kHeavyBig, false><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, in_queue + 1, a.nq_cap);
+    }
     count_launch(2);
+}
+
+void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st) { launch_query_heavy_impl(a, sm_count, st, false); }
+
+// feature-space sharding, origin side: sort-free fused passes, then the CTA tiers, all reading a.lists
+void launch_query_lists (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st)
+{
+    launch_query_warp_impl(a, T, sm_count, st, true);
+    launch_query_heavy_impl(a, sm_count, st, true);
 }
 
 // ---------------------------------------------------------------------------

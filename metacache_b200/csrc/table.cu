@@ -9,15 +9,17 @@
 //   serialize               hash_multimap.hpp:1037-1082
 #include "internal.h"
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
 namespace mcb {
 
 // ---------------------------------------------------------------------------
+template <class SizeT>
 __global__ void table_insert_kernel (Bucket* __restrict__ buckets, uint64_t nbuckets,
                                      const uint32_t* __restrict__ keys,
-                                     const uint8_t* __restrict__ sizes,
+                                     const SizeT* __restrict__ sizes,
                                      const uint64_t* __restrict__ offsets,
                                      const uint64_t* __restrict__ values, uint64_t nkeys,
                                      int* __restrict__ error)
@@ -48,7 +50,18 @@ void launch_table_insert (Bucket* buckets, uint64_t nbuckets, const uint32_t* ke
                           uint64_t nkeys, int* d_error, cudaStream_t st)
 {
     if (!nkeys) return;
-    table_insert_kernel<<<unsigned((nkeys + 255) / 256), 256, 0, st>>>(
+    table_insert_kernel<uint8_t><<<unsigned((nkeys + 255) / 256), 256, 0, st>>>(
+        buckets, nbuckets, keys, sizes, offsets, values, nkeys, d_error);
+    count_launch();
+}
+
+// merged buckets (several parts' locations of a feature in one bucket): sizes up to kSizeMask
+void launch_table_insert_wide (Bucket* buckets, uint64_t nbuckets, const uint32_t* keys,
+                               const uint32_t* sizes, const uint64_t* offsets, const uint64_t* values,
+                               uint64_t nkeys, int* d_error, cudaStream_t st)
+{
+    if (!nkeys) return;
+    table_insert_kernel<uint32_t><<<unsigned((nkeys + 255) / 256), 256, 0, st>>>(
         buckets, nbuckets, keys, sizes, offsets, values, nkeys, d_error);
     count_launch();
 }
@@ -122,7 +135,7 @@ __global__ void slot_sizes_kernel (const Bucket* __restrict__ buckets, uint64_t 
     if (i >= nslots) return;
     const Slot s = reinterpret_cast<const Slot*>(buckets)[i];
     occupied[i] = (s.meta != 0);
-    sizes[i] = s.meta & 0xFFu;
+    sizes[i] = s.meta & kSizeMask;
 }
 
 __global__ void slot_export_kernel (const Bucket* __restrict__ buckets, uint64_t nslots,
@@ -136,7 +149,7 @@ __global__ void slot_export_kernel (const Bucket* __restrict__ buckets, uint64_t
     if (i >= nslots) return;
     const Slot s = reinterpret_cast<const Slot*>(buckets)[i];
     if (s.meta == 0) return;
-    const uint32_t size = s.meta & 0xFFu;
+    const uint32_t size = s.meta & kSizeMask;
     const uint32_t kp = key_pos[i];
     out_keys[kp] = s.key;
     out_sizes[kp] = uint8_t(size);
@@ -202,6 +215,21 @@ __global__ void loc_max_kernel (const uint64_t* __restrict__ values, uint64_t n,
     if ((threadIdx.x & 31) == 0) { atomicMax(max_tgt_win, mt); atomicMax(max_tgt_win + 1, mw); }
 }
 
+// running maxima of target and window ids (out[0], out[1] are updated)
+int device_loc_max (const uint64_t* values, uint64_t n, uint32_t out[2], cudaStream_t st)
+{
+    if (!n) return 0;
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+    cudaMemcpyAsync(d, out, 8, cudaMemcpyHostToDevice, st);
+    loc_max_kernel<<<148 * 8, 256, 0, st>>>(values, n, d);
+    count_launch();
+    cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : -1;
+}
+
 __global__ void slot_caps_kernel (const Bucket* __restrict__ buckets, uint64_t nslots,
                                   uint32_t inline_cap, uint32_t line_elems, uint64_t* __restrict__ caps)
 {
@@ -209,7 +237,7 @@ __global__ void slot_caps_kernel (const Bucket* __restrict__ buckets, uint64_t n
     if (i > nslots) return;
     uint64_t c = 0;
     if (i < nslots) {
-        const uint32_t size = reinterpret_cast<const Slot*>(buckets)[i].meta & 0xFFu;
+        const uint32_t size = reinterpret_cast<const Slot*>(buckets)[i].meta & kSizeMask;
         if (size > inline_cap) c = (uint64_t(size) + line_elems - 1) / line_elems * line_elems;
     }
     caps[i] = c;                                  // caps[nslots] = 0: the scan leaves the total there
@@ -222,7 +250,7 @@ __global__ void slot_relayout_kernel (Bucket* __restrict__ buckets, uint64_t nsl
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     Slot* sl = reinterpret_cast<Slot*>(buckets) + i;
-    const uint32_t size = sl->meta & 0xFFu;
+    const uint32_t size = sl->meta & kSizeMask;
     if (size == 0) return;
     const uint64_t data = sl->data;
     auto pack = [win_bits] (uint64_t v) { return (uint32_t(v >> 32) << win_bits) | uint32_t(v); };
@@ -244,7 +272,8 @@ __global__ void slot_relayout_kernel (Bucket* __restrict__ buckets, uint64_t nsl
 static uint32_t bits_for (uint32_t maxval) { uint32_t b = 1; while (b < 32 && (maxval >> b)) ++b; return b; }
 
 int table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_values, uint64_t nvalues,
-                    void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st)
+                    void*& packed, uint64_t& packed_bytes, uint32_t& win_bits, cudaStream_t st,
+                    uint32_t at_least_tgt, uint32_t at_least_win)
 {
     packed = nullptr; packed_bytes = 0; win_bits = 0;
     const uint64_t nslots = nbuckets * 2;
@@ -262,7 +291,8 @@ int table_finalize (Bucket* buckets, uint64_t nbuckets, const uint64_t* raw_valu
     if (cudaMemcpyAsync(h_max, d_max, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) goto done;
     if (cudaStreamSynchronize(st) != cudaSuccess) goto done;
     {
-        const uint32_t tb = bits_for(h_max[0]), wb = bits_for(h_max[1]);
+        // shards of one database must agree on the packing: the caller passes the global maxima
+        const uint32_t tb = bits_for(std::max(h_max[0], at_least_tgt)), wb = bits_for(std::max(h_max[1], at_least_win));
         win_bits = (tb + wb <= 31) ? wb : 0u;     // top bit stays clear: ~0 is never a packed location
         if (getenv("MCB200_WIDE_LOCATIONS")) win_bits = 0;        // testing aid: force 64-bit locations
     }
@@ -409,6 +439,182 @@ done:
     if (rvalid) cudaFree(rvalid);
     if (nsel_d) cudaFree(nsel_d);
     if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+
+// ---------------------------------------------------------------------------
+// feature-space sharding at load time (one shard per GPU):
+//   shard_filter   keeps the keys of a `.cache` batch that this shard owns (shard_of)
+//   shard_merge    concatenates the buckets a key has in several source parts, in part order
+//                  ((tgt,win) order is kept: target ids ascend with the part) - what the reference's
+//                  multi-part query obtains by querying every part and merging per-part lists
+//                  (gpu_hashmap.cu:1255-1292; docs/partitioning.md:116-142)
+// ---------------------------------------------------------------------------
+__global__ void shard_flags_kernel (const uint32_t* __restrict__ keys, const uint8_t* __restrict__ sizes, uint64_t n,
+                                    uint32_t shard, uint32_t n_shards, uint32_t* __restrict__ kflag,
+                                    uint64_t* __restrict__ ksize)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const bool mine = i < n && shard_of(keys[i], n_shards) == shard && sizes[i] != 0;
+    kflag[i] = mine;                              // [n] = 0: the scans leave the totals there
+    ksize[i] = mine ? sizes[i] : 0u;
+}
+
+__global__ void shard_copy_kernel (const uint32_t* __restrict__ keys, const uint8_t* __restrict__ sizes,
+                                   const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ values, uint64_t n,
+                                   const uint32_t* __restrict__ kflag_raw, const uint32_t* __restrict__ kpos,
+                                   const uint64_t* __restrict__ vpos, uint32_t* __restrict__ okeys,
+                                   uint8_t* __restrict__ osizes, uint64_t* __restrict__ ovalues)
+{
+    // one warp per key: the (up to 254) values of a bucket are copied by the lanes
+    const uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    if (kpos[i + 1] == kpos[i]) return;           // not ours
+    const uint32_t lane = threadIdx.x & 31u, size = sizes[i];
+    if (lane == 0) { okeys[kpos[i]] = keys[i]; osizes[kpos[i]] = uint8_t(size); }
+    const uint64_t* src = values + in_off[i];
+    uint64_t* dst = ovalues + vpos[i];
+    for (uint32_t j = lane; j < size; j += 32) dst[j] = src[j];
+    (void)kflag_raw;
+}
+
+int shard_filter (const uint32_t* keys, const uint8_t* sizes, const uint64_t* values, uint64_t nkeys,
+                  uint32_t shard, uint32_t n_shards, BuiltPart& out, cudaStream_t st)
+{
+    int rc = 0;
+    out = BuiltPart{nullptr, nullptr, nullptr, 0, 0};
+    if (!nkeys) return 0;
+    if (nkeys >= (1ull << 32) - 2) return -2;
+    uint32_t *kflag = nullptr, *kpos = nullptr; uint64_t *ksize = nullptr, *vpos = nullptr, *in_off = nullptr;
+    void* tmp = nullptr; size_t tmpb = 0;
+    uint32_t nk = 0; uint64_t nv = 0;
+    const unsigned grid1 = unsigned((nkeys + 1 + 255) / 256);
+    CK(cudaMalloc(&kflag, (nkeys + 1) * 4)); CK(cudaMalloc(&kpos, (nkeys + 1) * 4));
+    CK(cudaMalloc(&ksize, (nkeys + 1) * 8)); CK(cudaMalloc(&vpos, (nkeys + 1) * 8));
+    CK(cudaMalloc(&in_off, (nkeys + 1) * 8));
+    shard_flags_kernel<<<grid1, 256, 0, st>>>(keys, sizes, nkeys, shard, n_shards, kflag, ksize);
+    count_launch();
+    device_scan_u32(kflag, kpos, nkeys + 1, tmp, tmpb, st);
+    device_scan_u64(ksize, vpos, nkeys + 1, tmp, tmpb, st);
+    device_scan_sizes(sizes, nkeys, 0, in_off, tmp, tmpb, st);
+    CK(cudaMemcpyAsync(&nk, kpos + nkeys, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nv, vpos + nkeys, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nk) {
+        CK(cudaMalloc(&out.keys, uint64_t(nk) * 4)); CK(cudaMalloc(&out.sizes, nk));
+        CK(cudaMalloc(&out.values, (nv ? nv : 1) * 8));
+        shard_copy_kernel<<<unsigned((nkeys * 32 + 255) / 256), 256, 0, st>>>(keys, sizes, in_off, values, nkeys, kflag,
+                                                                              kpos, vpos, out.keys, out.sizes, out.values);
+        count_launch();
+        CK(cudaStreamSynchronize(st));
+        out.nkeys = nk; out.nvalues = nv;
+    }
+done:
+    if (kflag) cudaFree(kflag);
+    if (kpos) cudaFree(kpos);
+    if (ksize) cudaFree(ksize);
+    if (vpos) cudaFree(vpos);
+    if (in_off) cudaFree(in_off);
+    if (tmp) cudaFree(tmp);
+    if (rc) { if (out.keys) cudaFree(out.keys); if (out.sizes) cudaFree(out.sizes); if (out.values) cudaFree(out.values);
+              out = BuiltPart{nullptr, nullptr, nullptr, 0, 0}; }
+    return rc;
+}
+
+__global__ void iota32_kernel (uint32_t* out, uint64_t n) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = uint32_t(i);
+}
+__global__ void gather_sizes_kernel (const uint8_t* __restrict__ sizes, const uint32_t* __restrict__ idx, uint64_t n,
+                                     uint64_t* __restrict__ out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = (i < n) ? sizes[idx[i]] : 0u;
+}
+__global__ void merged_runs_kernel (const uint32_t* __restrict__ rstart, const uint32_t* __restrict__ rlen, uint32_t nruns,
+                                    const uint64_t* __restrict__ go, uint32_t* __restrict__ usizes,
+                                    uint64_t* __restrict__ uoff, int* __restrict__ error) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint64_t b = go[rstart[r]], e = go[rstart[r] + rlen[r]];
+    if (e - b > kSizeMask) atomicExch(error, 4);
+    usizes[r] = uint32_t(e - b);
+    uoff[r] = b;
+}
+__global__ void merged_values_kernel (const uint8_t* __restrict__ sizes, const uint32_t* __restrict__ idx,
+                                      const uint64_t* __restrict__ voff, const uint64_t* __restrict__ go,
+                                      const uint64_t* __restrict__ values, uint64_t n, uint64_t* __restrict__ out) {
+    const uint64_t j = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n) return;
+    const uint32_t lane = threadIdx.x & 31u, src = idx[j], size = sizes[src];
+    const uint64_t* s = values + voff[src];
+    uint64_t* d = out + go[j];
+    for (uint32_t t = lane; t < size; t += 32) d[t] = s[t];
+}
+
+// keys/sizes/values: the filtered batches of all source parts concatenated in part order (consumed:
+// freed here).  out: unique keys with merged sizes (u32), offsets into the merged values.
+int shard_merge (uint32_t* keys, uint8_t* sizes, uint64_t* values, uint64_t nrec, uint64_t nvalues,
+                 MergedPart& out, int* d_error, cudaStream_t st)
+{
+    int rc = 0;
+    out = MergedPart{};
+    if (nrec >= (1ull << 32) - 2) return -2;
+    uint32_t *k1 = nullptr, *idx0 = nullptr, *idx1 = nullptr, *rlen = nullptr, *rstart = nullptr, *nruns_d = nullptr;
+    uint64_t *voff = nullptr, *go = nullptr;
+    void* tmp = nullptr; size_t tmpb = 0, need = 0;
+    uint32_t nruns = 0;
+    const unsigned grid = unsigned((nrec + 1 + 255) / 256);
+    if (nrec == 0) return 0;
+    CK(cudaMalloc(&voff, (nrec + 1) * 8));
+    device_scan_sizes(sizes, nrec, 0, voff, tmp, tmpb, st);
+    CK(cudaMalloc(&k1, nrec * 4)); CK(cudaMalloc(&idx0, nrec * 4)); CK(cudaMalloc(&idx1, nrec * 4));
+    iota32_kernel<<<grid, 256, 0, st>>>(idx0, nrec);
+    count_launch();
+    // stable: the records of a key stay in arrival (= part) order
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, k1, idx0, idx1, int64_t(nrec), 0, 32, st);
+    ensure_tmp(tmp, tmpb, need);
+    CK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, k1, idx0, idx1, int64_t(nrec), 0, 32, st));
+    count_launch(8);
+    CK(cudaStreamSynchronize(st));
+    cudaFree(keys); keys = nullptr; cudaFree(idx0); idx0 = nullptr;
+    CK(cudaMalloc(&go, (nrec + 1) * 8));
+    gather_sizes_kernel<<<grid, 256, 0, st>>>(sizes, idx1, nrec, go);
+    count_launch();
+    device_scan_u64(go, go, nrec + 1, tmp, tmpb, st);
+    CK(cudaMalloc(&out.keys, nrec * 4)); CK(cudaMalloc(&rlen, nrec * 4)); CK(cudaMalloc(&nruns_d, 4));
+    need = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, need, k1, out.keys, rlen, nruns_d, int64_t(nrec), st);
+    ensure_tmp(tmp, tmpb, need);
+    CK(cub::DeviceRunLengthEncode::Encode(tmp, need, k1, out.keys, rlen, nruns_d, int64_t(nrec), st));
+    count_launch(2);
+    CK(cudaMemcpyAsync(&nruns, nruns_d, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(k1); k1 = nullptr;
+    CK(cudaMalloc(&rstart, (uint64_t(nruns) + 1) * 4));
+    device_scan_u32(rlen, rstart, nruns, tmp, tmpb, st);
+    CK(cudaMalloc(&out.sizes, uint64_t(nruns) * 4)); CK(cudaMalloc(&out.offsets, uint64_t(nruns) * 8));
+    merged_runs_kernel<<<(nruns + 255) / 256, 256, 0, st>>>(rstart, rlen, nruns, go, out.sizes, out.offsets, d_error);
+    CK(cudaMalloc(&out.values, (nvalues ? nvalues : 1) * 8));
+    merged_values_kernel<<<unsigned((nrec * 32 + 255) / 256), 256, 0, st>>>(sizes, idx1, voff, go, values, nrec, out.values);
+    count_launch(2);
+    CK(cudaStreamSynchronize(st));
+    out.nkeys = nruns; out.nvalues = nvalues;
+done:
+    if (keys) cudaFree(keys);
+    cudaFree(sizes); cudaFree(values);
+    if (k1) cudaFree(k1);
+    if (idx0) cudaFree(idx0);
+    if (idx1) cudaFree(idx1);
+    if (rlen) cudaFree(rlen);
+    if (rstart) cudaFree(rstart);
+    if (nruns_d) cudaFree(nruns_d);
+    if (voff) cudaFree(voff);
+    if (go) cudaFree(go);
+    if (tmp) cudaFree(tmp);
+    if (rc) { if (out.keys) cudaFree(out.keys); if (out.sizes) cudaFree(out.sizes); if (out.offsets) cudaFree(out.offsets);
+              if (out.values) cudaFree(out.values); out = MergedPart{}; }
     return rc;
 }
 
