@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--replicate", action="store_true",
                     help="N > 1: every GPU holds the SAME single-part database and queries only its own reads "
                          "(the reference's -replicate mode, SURVEY 8e) instead of the target-sharded database")
+    ap.add_argument("--shard-by", default="feature", choices=["feature", "target"],
+                    help="N > 1: feature = every GPU owns a slice of the FEATURE space with the locations of all parts "
+                         "(one table access per feature however many GPUs; default); target = the reference's own "
+                         "partitioning, every GPU probes every read against its part (capacity mode / parity oracle)")
+    ap.add_argument("--chunk-reads", type=int, default=1_250_000, help="reads per pipeline chunk of the feature-sharded step")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default)")
     ap.add_argument("--cache", default=os.environ.get(
@@ -142,6 +147,39 @@ def build_part(args, part, device):
     info = dict(build_s=round(time.time() - t0, 2), keys=db.key_count(0), locations=db.value_count(0),
                 table_gb=round(db.device_bytes(0) / 1e9, 2))
     return db, bases, wins, info
+
+
+def build_feature_shard(args, rank, world, device):
+    """Shard `rank` of the feature-sharded database: every rank generates and sketches EVERY part
+    (no exchange at load time; ~1 s per part) and keeps the features it owns, with the locations of
+    all parts merged per feature.  Returns the bases of part `rank` for the read generator."""
+    import torch
+    from metacache_b200 import _lib, synth
+    from metacache_b200.database import Database
+    from metacache_b200.distributed import TorchComm, load_feature_shard
+    from metacache_b200._lib import Sketching
+    t0 = time.time()
+    db = Database(device.index, 1)
+    sk = Sketching(**SK)
+    keep = {}
+
+    def feed(d):
+        for p in range(world):
+            bases, off = synth.make_targets(args.targets, args.target_len, 10, synth.SEED_DB + p, device=device)
+            wins = np.zeros(args.targets, np.uint32)
+            _lib.check(_lib.lib().mcb200_db_build_part_from_targets(
+                d._h, 0, bases.data_ptr(), off.data_ptr(), args.targets, p * args.targets, C.byref(sk), 254,
+                args.load_factor, wins.ctypes.data))
+            if p == rank:
+                keep["bases"], keep["wins"] = bases, wins
+            del bases, off
+            torch.cuda.empty_cache()
+
+    load_feature_shard(db, rank, world, world * args.targets, feed, TorchComm(), args.load_factor)
+    torch.cuda.synchronize(device)
+    info = dict(build_s=round(time.time() - t0, 2), keys=db.key_count(0), locations=db.value_count(0),
+                table_gb=round(db.device_bytes(0) / 1e9, 2), shard="features of all %d parts owned by this rank" % world)
+    return db, keep["bases"], keep["wins"], info
 
 
 def make_reads(args, bases, rank, device):
@@ -359,6 +397,17 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                    "ASCII buffers to candidates in host memory (query_batch seam)"}
 
 
+def phase_breakdown(events, steps):
+    """FeatureShardedQuery timing marks -> ms per step and phase, summed over the chunks of a step: time
+    from the previous mark on the chunk's stream (waiting for the host and for other chunks included)"""
+    acc, last = {}, {}
+    for chunk, name, ev in events:
+        if name != "start" and chunk in last:
+            acc[name] = acc.get(name, 0.0) + last[chunk].elapsed_time(ev)
+        last[chunk] = ev
+    return {k: v / steps for k, v in acc.items()}
+
+
 def reference_sample(args, nq, threads, per_read_scale):
     return args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads) * per_read_scale))
 
@@ -447,14 +496,20 @@ def main():
         args.reads = 10_000_000 if args.workload == "C2" else 2_000_000
     if args.workload == "C3" and sharded:
         raise SystemExit("workload C3 is a single-GPU configuration (BASELINE.json configs[2]); use --replicate for N > 1")
-    db, bases, wins, dbinfo = build_part(args, part, device)
+    by_feature = sharded and args.shard_by == "feature"
+    if by_feature:
+        db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device)
+    else:
+        db, bases, wins, dbinfo = build_part(args, part, device)
     flat, offs = make_reads(args, bases, rank, device)       # uint8 bases back to back + int64 offsets, on the device
     del bases
     torch.cuda.empty_cache()
     nq = args.reads
     n_bases = int(offs[-1].item())
     part_desc = ("single partition" if world == 1 else
-                 f"{world}-way target-partitioned, one part per GPU" if sharded else
+                 f"{world}-way target-partitioned database ({world * args.targets} targets) sharded by FEATURE over "
+                 f"{world} GPUs, features and location lists exchanged over NCCL" if by_feature else
+                 f"{world}-way target-partitioned, one part per GPU, every GPU probes every read" if sharded else
                  f"single partition replicated on {world} GPUs, every GPU queries its own reads")
     if args.workload == "C2":
         metric = "reads_per_second_150bp"
@@ -468,7 +523,7 @@ def main():
         read_len = round(n_bases / nq, 1)
     config = {"workload": workload, "reads_per_gpu": nq, "read_len": read_len, "targets_per_part": args.targets,
               "db": dbinfo, "l2": "inputs larger than L2 (reads %.1f GB + table %.1f GB per step)" %
-              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": ("db-sharded x%d" if sharded or world == 1 else "replicas x%d") % world}
+              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": ("feature-sharded x%d" if by_feature else "db-sharded x%d" if sharded or world == 1 else "replicas x%d") % world}
     per_read_scale = READ_LEN * nq / n_bases                 # CPU samples are sized in 150 bp read equivalents
 
     if args.prepare_reference:
@@ -503,6 +558,17 @@ def main():
     if not sharded:
         def step():
             _lib.check(L.mcb200_query_device(ws, C.byref(q), C.byref(sk), d_top.data_ptr(), sp))
+    elif by_feature:
+        from metacache_b200.distributed import DeviceBackend, FeatureShardedQuery, TorchComm, feature_sharded_step
+        chunk = min(args.chunk_reads, nq)
+        fstreams = [torch.cuda.Stream(device) for _ in range(3)]
+        backend = DeviceBackend(db, world, chunk, MAXC, device)
+        fq = FeatureShardedQuery(backend, TorchComm(), SK["sketchlen"], MAXC, chunk_queries=chunk, n_slots=3,
+                                 streams=fstreams)
+
+        def step():
+            with torch.cuda.stream(stream):
+                feature_sharded_step(fq, ws, q, sk, max_win, d_top)
     else:
         from metacache_b200.distributed import ShardedQuery
         nwin = 2 * nq                            # 150 bp reads: two windows each
@@ -521,7 +587,10 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    nwin_launch = L.mcb200_workspace_num_windows(ws) if not sharded else 2 * nq
+    nwin_launch = L.mcb200_workspace_num_windows(ws) if (not sharded or by_feature) else 2 * nq
+    if by_feature:
+        fq.enable_timing(True)
+        fq.stats.update(features_sent=0, locations_received=0, chunks=0)
     cnt = (C.c_uint64 * 8)()
     _lib.check(L.mcb200_workspace_counters(ws, cnt))         # resets the counters
     _lib.check(L.mcb200_workspace_set_profiling(ws, 1))
@@ -537,6 +606,10 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = L.mcb200_kernel_launches() - launches0
+    phases = None
+    if by_feature:
+        phases = phase_breakdown(fq.events, args.steps)
+        fq.enable_timing(False)
     stage = (C.c_float * 8)()
     _lib.check(L.mcb200_workspace_stage_times(ws, stage))
     _lib.check(L.mcb200_workspace_set_profiling(ws, 0))
@@ -545,6 +618,8 @@ def main():
     # rows of the first reads, kept for the bit-exact comparison with the reference below
     keep = int(min(nq, max(200_000, 100_000 * threads) * per_read_scale)) if not args.cpu_sample else args.cpu_sample
     top_first = d_top[:keep].cpu().numpy() if not sharded else None
+    if by_feature and os.environ.get("MCB200_BENCH_DUMP_TOPS"):
+        np.save(os.environ["MCB200_BENCH_DUMP_TOPS"] + f".r{rank}.npy", d_top[:200_000].cpu().numpy())
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -597,6 +672,24 @@ def main():
                 "queries_fused_warp": int(cnt[0] / n_launch), "queries_cta_smem": int(cnt[1] / n_launch),
                 "queries_cta_global": int(cnt[2] / n_launch)}
 
+    if by_feature:
+        f_sent = fq.stats["features_sent"] / calls
+        l_recv = fq.stats["locations_received"] / calls
+        p_ms = phases["probe"]
+        pb = f_sent * 32.0                                       # 4 B feature in, 16 B slot, 4 + 8 B out (per rank ~ balanced)
+        roofline = {"bound": "hbm", "kernel": "shard_probe_kernel (+ scan): owner-side slot lookup, one thread per feature",
+                    "achieved": round(pb / (p_ms * 1e-3) / 1e9, 1) if p_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                    "frac": round(pb / (p_ms * 1e-3) / 1e9 / peak, 4) if p_ms > 0 else 0.0, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "alg_bytes_per_launch": int(pb), "kernel_ms_per_launch": round(p_ms, 3),
+                    "note": "rank 0; kernels of different chunks overlap on the GPU, so per-phase times are upper bounds",
+                    "phase_ms_per_step": {k_: round(v, 3) for k_, v in phases.items()},
+                    "stage_ms_per_step": {"encode": round(stage[0] / calls, 3), "window_tables": round(stage[1] / calls, 3),
+                                          "sketch": round(stage[2] / calls, 3)},
+                    "per_read": {"features_routed": round(f_sent / nq, 2), "locations_returned": round(l_recv / nq, 2)},
+                    "exchange_bytes_per_step_per_rank": int(f_sent * 8 + l_recv * backend.loc_bytes),
+                    "chunks_per_step": int(fq.stats["chunks"] / calls)}
+
     # ---------------- e2e: host buffers through the batch API (H2D + kernels + D2H) -----------
     e2e = None
     if not sharded:
@@ -641,7 +734,8 @@ def main():
         e2e_ms = float(t.item()) / args.steps
         e2e = {"value": nq_total / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(n_bases * world),
                "d2h_bytes_per_step": int(nq * MAXC * 16 * world), "ms_per_step": round(e2e_ms, 3),
-               "api": "pinned host reads -> H2D -> sketch/all-gather/probe/all-to-all/merge -> D2H"}
+               "api": "pinned host reads -> H2D -> " + ("sketch / route / all-to-all / probe / gather / all-to-all / reduce"
+                                                          if by_feature else "sketch/all-gather/probe/all-to-all/merge") + " -> D2H"}
 
     clk = clocks.stop()                                      # sampled through both timed regions (value and e2e)
 

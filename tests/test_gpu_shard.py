@@ -44,7 +44,7 @@ def _run_threads(world, fn):
     return res
 
 
-def _rank(comm, rank, world, reads, chunk, g1, parts, n_targets, force_wide=False):
+def _rank(comm, rank, world, reads, chunk, g1, parts, n_targets, device_index=0):
     import torch
     from metacache_b200 import _lib
     from metacache_b200._lib import Sketching
@@ -52,9 +52,9 @@ def _rank(comm, rank, world, reads, chunk, g1, parts, n_targets, force_wide=Fals
     from metacache_b200.distributed import (DeviceBackend, DeviceReads, FeatureShardedQuery, feature_sharded_step,
                                             load_feature_shard)
     L = _lib.lib()
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", device_index)
     torch.cuda.set_device(dev)
-    db = Database(0, 1)
+    db = Database(device_index, 1)
 
     def feed(d):
         for p in parts:
