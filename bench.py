@@ -397,17 +397,6 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                    "ASCII buffers to candidates in host memory (query_batch seam)"}
 
 
-def phase_breakdown(events, steps):
-    """FeatureShardedQuery timing marks -> ms per step and phase, summed over the chunks of a step: time
-    from the previous mark on the chunk's stream (waiting for the host and for other chunks included)"""
-    acc, last = {}, {}
-    for chunk, name, ev in events:
-        if name != "start" and chunk in last:
-            acc[name] = acc.get(name, 0.0) + last[chunk].elapsed_time(ev)
-        last[chunk] = ev
-    return {k: v / steps for k, v in acc.items()}
-
-
 def reference_sample(args, nq, threads, per_read_scale):
     return args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads) * per_read_scale))
 
@@ -608,7 +597,7 @@ def main():
     launches = L.mcb200_kernel_launches() - launches0
     phases = None
     if by_feature:
-        phases = phase_breakdown(fq.events, args.steps)
+        phases = {k_: v / args.steps for k_, v in fq.phase_ms().items()}
         fq.enable_timing(False)
     stage = (C.c_float * 8)()
     _lib.check(L.mcb200_workspace_stage_times(ws, stage))
@@ -682,7 +671,8 @@ def main():
                     "frac": round(pb / (p_ms * 1e-3) / 1e9 / peak, 4) if p_ms > 0 else 0.0, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "alg_bytes_per_launch": int(pb), "kernel_ms_per_launch": round(p_ms, 3),
-                    "note": "rank 0; kernels of different chunks overlap on the GPU, so per-phase times are upper bounds",
+                    "note": "rank 0; CUDA events around each operation on its chunk's stream, summed over the chunks of a step; "
+                            "operations of different chunks overlap on the GPU, so the sum exceeds the step",
                     "phase_ms_per_step": {k_: round(v, 3) for k_, v in phases.items()},
                     "stage_ms_per_step": {"encode": round(stage[0] / calls, 3), "window_tables": round(stage[1] / calls, 3),
                                           "sketch": round(stage[2] / calls, 3)},

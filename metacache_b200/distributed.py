@@ -273,22 +273,42 @@ class FeatureShardedQuery:
     def enable_timing(self, on=True):
         self.events = [] if on else None
 
-    def _mark(self, slot, chunk, name):
-        if self.events is not None and self.streams is not None:
-            ev = self.b.torch.cuda.Event(enable_timing=True)
-            ev.record(self.streams[slot])
-            self.events.append((chunk, name, ev))
+    def _timed(self, slot, name):
+        """context: CUDA events on the slot's stream around the operations enqueued inside"""
+        import contextlib
+        if self.events is None or self.streams is None:
+            return contextlib.nullcontext()
+        fq, torch = self, self.b.torch
+
+        class _T:
+            def __enter__(self_):
+                self_.e0 = torch.cuda.Event(enable_timing=True)
+                self_.e0.record(fq.streams[slot])
+
+            def __exit__(self_, *exc):
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(fq.streams[slot])
+                fq.events.append((name, self_.e0, e1))
+        return _T()
+
+    def phase_ms(self):
+        """sum of the recorded intervals per operation (call after a synchronisation; clears them)"""
+        acc = {}
+        for name, e0, e1 in self.events or []:
+            acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        if self.events is not None:
+            self.events = []
+        return acc
 
     # ---- the three phases of one chunk --------------------------------------------------
     def _phase_a(self, st):
         torch = self.b.torch
         N, nq, slot = self.N, st["nq"], st["slot"]
         with self._on(slot):
-            self._mark(slot, st["c"], "start")
             pos = self._buf(slot, "pos", N * (nq + 1) + 1, torch.int32)
             send = self._buf(slot, "send", st["feat_cap"], torch.int32)
-            self.b.route(slot, st["feats"], st["qwo"], nq, self.S, pos, send)
-            self._mark(slot, st["c"], "route")
+            with self._timed(slot, "route"):
+                self.b.route(slot, st["feats"], st["qwo"], nq, self.S, pos, send)
             seg_idx = torch.arange(N + 1, dtype=torch.int64, device=pos.device) * (nq + 1)
             seg = pos[seg_idx].to(torch.int64)                  # N + 1 segment starts
             st["pos"], st["send"] = pos, send
@@ -297,22 +317,28 @@ class FeatureShardedQuery:
     def _phase_b(self, st):
         torch = self.b.torch
         N, slot = self.N, st["slot"]
-        M = st.pop("pend_a").result()                           # M[g][o]: features g sends to o
+        pend = st.pop("pend_a")
+        M = pend.result()                                       # M[g][o]: features g sends to o
         st["send_counts"] = M[self.rank].copy()
         st["recv_counts"] = M[:, self.rank].copy()
         nrecv = int(st["recv_counts"].sum())
         st["nrecv"] = nrecv
         with self._on(slot):
             recv = self._buf(slot, "recv", nrecv, torch.int32)
-            self.comm.all_to_all(recv[:nrecv], st["send"][:int(st["send_counts"].sum())],
-                                 st["recv_counts"], st["send_counts"])
-            self._mark(slot, st["c"], "exchange_features")
+            with self._timed(slot, "exchange_features"):
+                self.comm.all_to_all(recv[:nrecv], st["send"][:int(st["send_counts"].sum())],
+                                     st["recv_counts"], st["send_counts"])
             off = self._buf(slot, "off", nrecv + 1, torch.int32)
             data = self._buf(slot, "data", nrecv, torch.int64)
-            self.b.probe(slot, recv, nrecv, off, data)
-            self._mark(slot, st["c"], "probe")
-            bounds = torch.as_tensor(np.concatenate([[0], np.cumsum(st["recv_counts"])]), dtype=torch.int64)
-            segoff = off[bounds.to(off.device)].to(torch.int64)  # N + 1 location offsets at the origin boundaries
+            with self._timed(slot, "probe"):
+                self.b.probe(slot, recv, nrecv, off, data)
+            # location offsets at the origin boundaries, computed where the counts already are (no host copy)
+            if pend.keep is not None:
+                rc = pend.keep[:, self.rank]
+            else:
+                rc = torch.as_tensor(st["recv_counts"], dtype=torch.int64).to(off.device)
+            bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=off.device), torch.cumsum(rc, 0)])
+            segoff = off[bounds].to(torch.int64)
             st["off"], st["data"] = off, data
             st["pend_b"] = self.comm.all_gather_counts(segoff[1:] - segoff[:-1])
         self.stats["features_sent"] += int(st["send_counts"].sum())
@@ -328,22 +354,22 @@ class FeatureShardedQuery:
             raise _lib.Mcb200Error(None, "more than 2^32 locations in one chunk: use smaller chunks")
         with self._on(slot):
             locs = self._buf(slot, "locs", nsend, self.b.loc_dtype)
-            self.b.gather(slot, st["off"], st["data"], st["nrecv"], locs)
-            self._mark(slot, st["c"], "gather")
+            with self._timed(slot, "gather"):
+                self.b.gather(slot, st["off"], st["data"], st["nrecv"], locs)
             rlocs = self._buf(slot, "rlocs", nrecv_l, self.b.loc_dtype)
-            self.comm.all_to_all(rlocs[:nrecv_l], locs[:nsend], loc_recv, loc_send)
             nfs = int(st["send_counts"].sum())
             roff = self._buf(slot, "roff", nfs, torch.int32)
-            self.comm.all_to_all(roff[:nfs], st["off"][:st["nrecv"]], st["send_counts"], st["recv_counts"])
-            self._mark(slot, st["c"], "exchange_locations")
+            with self._timed(slot, "exchange_locations"):
+                self.comm.all_to_all(rlocs[:nrecv_l], locs[:nsend], loc_recv, loc_send)
+                self.comm.all_to_all(roff[:nfs], st["off"][:st["nrecv"]], st["send_counts"], st["recv_counts"])
             runs, fo, lo = [], 0, 0
             for o in range(N):
                 nf, nl = int(st["send_counts"][o]), int(loc_recv[o])
                 runs.append((rlocs[lo:lo + max(nl, 1)], roff[fo:fo + max(nf, 1)], nf, nl))
                 fo += nf
                 lo += nl
-            self.b.reduce(slot, st["pos"], runs, st["max_win"], nq, top[st["q0"]:st["q0"] + nq])
-            self._mark(slot, st["c"], "reduce")
+            with self._timed(slot, "reduce"):
+                self.b.reduce(slot, st["pos"], runs, st["max_win"], nq, top[st["q0"]:st["q0"] + nq])
         self.stats["locations_received"] += nrecv_l
         self.stats["chunks"] += 1
 
