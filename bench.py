@@ -58,6 +58,7 @@ def parse():
                     help="N > 1: feature = every GPU owns a slice of the FEATURE space with the locations of all parts "
                          "(one table access per feature however many GPUs; default); target = the reference's own "
                          "partitioning, every GPU probes every read against its part (capacity mode / parity oracle)")
+    ap.add_argument("--shard-streams", type=int, default=3, help="CUDA streams of the feature-sharded chunk pipeline (1 = every operation serial, for profiling)")
     ap.add_argument("--chunk-reads", type=int, default=1_250_000, help="reads per pipeline chunk of the feature-sharded step")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default)")
@@ -550,10 +551,11 @@ def main():
     elif by_feature:
         from metacache_b200.distributed import DeviceBackend, FeatureShardedQuery, TorchComm, feature_sharded_step
         chunk = min(args.chunk_reads, nq)
-        fstreams = [torch.cuda.Stream(device) for _ in range(3)]
+        fstreams = [torch.cuda.Stream(device) for _ in range(max(1, min(3, args.shard_streams)))]
+        fstreams = [fstreams[i % len(fstreams)] for i in range(3)]
         backend = DeviceBackend(db, world, chunk, MAXC, device)
-        fq = FeatureShardedQuery(backend, TorchComm(), SK["sketchlen"], MAXC, chunk_queries=chunk, n_slots=3,
-                                 streams=fstreams)
+        fq = FeatureShardedQuery(backend, TorchComm(), SK["sketchlen"], MAXC, chunk_queries=chunk,
+                                 n_slots=3, streams=fstreams)
 
         def step():
             with torch.cuda.stream(stream):

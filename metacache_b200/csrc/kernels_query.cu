@@ -803,6 +803,9 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
             else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t, false>, kQWarps * 32, smem);
             if (per_sm < 1) per_sm = 1;
             if (pass == 0 && cap >= 1 && cap < per_sm) per_sm = cap;
+            // sharded mode: the persistent CTAs must not fill the SMs completely, or the NCCL kernels and the
+            // owner-side kernels of the next chunk (other streams) could not start before this kernel ends
+            if (lists && per_sm > 2) per_sm -= 1;
             const unsigned pgrid = std::min<unsigned>(grid, unsigned(sm_count * per_sm));
             const int in_queue = pass == 0 ? -1 : 0;
             if (lists) {

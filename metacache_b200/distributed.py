@@ -121,9 +121,31 @@ class TorchComm:
             ev.record()
         return _Pending(host, ev, out)
 
-    def all_to_all(self, out, inp, out_splits, in_splits):
-        self.dist.all_to_all_single(out, inp, [int(x) for x in out_splits], [int(x) for x in in_splits],
-                                    group=self.group)
+    def all_to_all(self, out, inp, out_splits, in_splits, local="copy"):
+        """variable all-to-all; the segment a rank sends to itself never enters NCCL: it is copied
+        directly (local="copy") or left to the caller, who reads it in place (local="skip")"""
+        osp, isp = [int(x) for x in out_splits], [int(x) for x in in_splits]
+        r = self.rank
+        if self.world == 1:
+            if local == "copy":
+                out[:osp[0]].copy_(inp[:isp[0]])
+            return
+        o0, i0 = sum(osp[:r]), sum(isp[:r])
+        if local == "copy" and osp[r]:
+            out[o0:o0 + osp[r]].copy_(inp[i0:i0 + isp[r]], non_blocking=True)
+        # the remote segments: one batch of point-to-point operations (a single NCCL group)
+        ops, oo, ii = [], 0, 0
+        for j in range(self.world):
+            if j != r:
+                if isp[j]:
+                    ops.append(self.dist.P2POp(self.dist.isend, inp[ii:ii + isp[j]], j, group=self.group))
+                if osp[j]:
+                    ops.append(self.dist.P2POp(self.dist.irecv, out[oo:oo + osp[j]], j, group=self.group))
+            oo += osp[j]
+            ii += isp[j]
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
 
 
 class _Pending:
@@ -164,7 +186,7 @@ class ThreadComm:
         rows = self._exchange(counts.cpu())
         return _Pending(self.torch.stack(rows), None, None)
 
-    def all_to_all(self, out, inp, out_splits, in_splits):
+    def all_to_all(self, out, inp, out_splits, in_splits, local="copy"):
         if inp.is_cuda:
             self.torch.cuda.current_stream().synchronize()
         parts = list(self.torch.split(inp, [int(x) for x in in_splits]))
@@ -192,6 +214,7 @@ class DeviceBackend:
         self.loc_dtype = torch.int32 if self.loc_bytes == 4 else torch.int64
         self.max_chunk = max_chunk_queries
         self._ws = {}
+        self._cap = {}
 
     def ws(self, slot):
         if slot not in self._ws:
@@ -224,8 +247,14 @@ class DeviceBackend:
         _lib.check(self.L.mcb200_shard_gather_device(self.ws(slot), 0, off.data_ptr(), data.data_ptr(), n,
                                                      locs.data_ptr(), self._sp()))
 
-    def reduce(self, slot, pos, runs, max_win, nq, top):
+    def reduce(self, slot, pos, runs, max_win, nq, top, mean_locations=0.0):
         """runs: list of (locs tensor, off tensor, n_features, n_locations) per owner"""
+        # first-pass table of the fused reduction: large databases return many unrelated single hits
+        # (distinct locations), so size it by the mean list length instead of overflowing to the second pass
+        cap = 256 if mean_locations < 160 else (512 if mean_locations < 320 else 1024)
+        if self._cap.get(slot) != cap:
+            _lib.check(self.L.mcb200_workspace_set_warp_capacity(self.ws(slot), cap))
+            self._cap[slot] = cap
         arr = (_lib.ShardRun * self.N)()
         for o, (locs, off, nf, nl) in enumerate(runs):
             arr[o] = _lib.ShardRun(locs.data_ptr(), off.data_ptr(), int(nf), int(nl))
@@ -360,16 +389,24 @@ class FeatureShardedQuery:
             nfs = int(st["send_counts"].sum())
             roff = self._buf(slot, "roff", nfs, torch.int32)
             with self._timed(slot, "exchange_locations"):
-                self.comm.all_to_all(rlocs[:nrecv_l], locs[:nsend], loc_recv, loc_send)
-                self.comm.all_to_all(roff[:nfs], st["off"][:st["nrecv"]], st["send_counts"], st["recv_counts"])
+                # what this rank returns to itself is read in place by the reduction (no copy, no NCCL)
+                self.comm.all_to_all(rlocs[:nrecv_l], locs[:nsend], loc_recv, loc_send, local="skip")
+                self.comm.all_to_all(roff[:nfs], st["off"][:st["nrecv"]], st["send_counts"], st["recv_counts"],
+                                     local="skip")
             runs, fo, lo = [], 0, 0
+            me = self.rank
+            own_l0, own_f0 = int(loc_send[:me].sum()), int(st["recv_counts"][:me].sum())
             for o in range(N):
                 nf, nl = int(st["send_counts"][o]), int(loc_recv[o])
-                runs.append((rlocs[lo:lo + max(nl, 1)], roff[fo:fo + max(nf, 1)], nf, nl))
+                if o == me:
+                    runs.append((locs[own_l0:own_l0 + max(nl, 1)], st["off"][own_f0:own_f0 + max(nf, 1)], nf, nl))
+                else:
+                    runs.append((rlocs[lo:lo + max(nl, 1)], roff[fo:fo + max(nf, 1)], nf, nl))
                 fo += nf
                 lo += nl
             with self._timed(slot, "reduce"):
-                self.b.reduce(slot, st["pos"], runs, st["max_win"], nq, top[st["q0"]:st["q0"] + nq])
+                self.b.reduce(slot, st["pos"], runs, st["max_win"], nq, top[st["q0"]:st["q0"] + nq],
+                              mean_locations=nrecv_l / max(nq, 1))
         self.stats["locations_received"] += nrecv_l
         self.stats["chunks"] += 1
 

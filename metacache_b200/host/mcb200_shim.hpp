@@ -32,8 +32,34 @@
 #include <mutex>
 #include <fstream>
 #include <exception>
+#include <cstdlib>
+#include <ostream>
+#include <algorithm>
 
 #include "../../include/mcb200.h"
+
+#ifdef MCB200_IN_REFERENCE_TREE
+// Compiled INSIDE the reference tree: src/gpu_hashmap.cuh and src/query_batch.cuh
+// are two-line forwarding headers that define this macro and include this file; the seam classes then
+// speak the reference's OWN types, and the rest of the tree compiles unchanged with -DGPU_MODE.
+#include "config.hpp"
+#include "candidate_structs.hpp"
+#include "cmdline_utility.hpp"
+#include "hash_dna.hpp"
+#include "span.hpp"
+#include "stat_combined.hpp"
+#include "taxonomy.hpp"
+
+namespace mcb200 {
+using mc::part_id; using mc::target_id; using mc::window_id;
+using feature = std::uint32_t;
+using sketching_opt = mc::sketching_opt;
+using mc::window_range; using mc::match_candidate; using mc::candidate_generation_rules;
+using tax_pointer = const mc::taxon*;
+template <class T> using span = mc::span<const T>;
+template <class T> inline span<T> make_span (const T* p, std::size_t n) { return span<T>(p, n); }
+struct location { window_id win; target_id tgt; };    // only the default template argument below
+#else
 
 namespace mcb200 {
 
@@ -41,6 +67,7 @@ using part_id   = std::uint32_t;        // config.hpp
 using target_id = std::uint32_t;
 using window_id = std::uint32_t;
 using feature   = std::uint32_t;
+using tax_pointer = const void*;        // const taxon* in the reference
 
 /** database.hpp:136-166 */
 struct location {
@@ -69,7 +96,6 @@ struct match_candidate {
     std::uint32_t hits;
     window_range  pos;
 };
-static_assert(sizeof(match_candidate) == 24, "match_candidate must be 24 bytes like the reference's");
 
 /** candidate_structs.hpp:110-125 */
 struct candidate_generation_rules {
@@ -87,6 +113,9 @@ template <class T> struct span {
     bool empty () const noexcept { return n == 0; }
     const T& operator [] (std::size_t i) const noexcept { return ptr[i]; }
 };
+template <class T> inline span<T> make_span (const T* p, std::size_t n) { return span<T>{p, n}; }
+#endif
+static_assert(sizeof(match_candidate) == 24, "match_candidate must be 24 bytes like the reference's");
 
 [[noreturn]] inline void throw_last (const char* what) {
     throw std::runtime_error(std::string(what) + ": " + mcb200_last_error());
@@ -104,13 +133,20 @@ public:
     using value_type         = ValueT;
     using bucket_size_type   = std::uint8_t;
     using feature_count_type = std::uint64_t;
-    using taxon_rank         = int;
-    /** taxonomy::ranked_lineage reduced to opaque pointers, index = rank (taxonomy.hpp:368) */
-    using ranked_lineage     = std::array<const void*, 21>;
+    using size_type          = std::uint64_t;
+    /** taxonomy::ranked_lineage (taxonomy.hpp:368): one taxon pointer per rank (opaque outside the tree) */
+    using ranked_lineage     = std::array<tax_pointer, 21>;
 
-    explicit gpu_hashmap (int device = 0) : device_(device) {}
+    /** gpu_hashmap() (gpu_hashmap.cuh:110); the device is ours: MCB200_DEVICE or 0 */
+    gpu_hashmap () : device_(default_device()) {}
+    explicit gpu_hashmap (int device) : device_(device) {}
     gpu_hashmap (const gpu_hashmap&) = delete;
+    gpu_hashmap (gpu_hashmap&& o) noexcept
+        : device_(o.device_), db_(o.db_), maxLoadFactor_(o.maxLoadFactor_), maxLoc_(o.maxLoc_),
+          lineages_(std::move(o.lineages_)), taxRank_(o.taxRank_)
+    { o.db_ = nullptr; if (current() == &o) current() = this; }
     ~gpu_hashmap () { if (db_) mcb200_db_close(db_); if (current() == this) current() = nullptr; }
+    static int default_device () { const char* e = std::getenv("MCB200_DEVICE"); return e ? std::atoi(e) : 0; }
 
     /** the store queries are bound to when a query_batch is created without one */
     static gpu_hashmap*& current () { static gpu_hashmap* c = nullptr; return c; }
@@ -122,12 +158,23 @@ public:
         if (!db_) throw_last("prepare_query_tables");
         current() = this;
     }
-    unsigned table_count () const noexcept { return db_ ? mcb200_db_part_count(db_) : 0; }
+    part_id table_count () const noexcept { return db_ ? part_id(mcb200_db_part_count(db_)) : 0; }
+    part_id gpu_count () const noexcept { return 1; }
     void enable_peer_access () {}     // one process per GPU: no peer chain (gpu_hashmap.cu:1403-1420)
+    void pop_status () {}
+    void pop_status (part_id) {}
 
     /** read_binary(istream&, store&, part_id, progress) (gpu_hashmap.cu:813-912):
      *  the `.cache` stream positioned at its start */
-    friend void read_binary (std::istream& is, gpu_hashmap& m, part_id partId) {
+    friend void read_binary (std::istream& is, gpu_hashmap& m, part_id partId) { int none = 0; m.deserialize(is, partId, none); }
+    /** the reference's overload: progress = concurrent_progress (cmdline_utility.hpp:62), advanced per batch */
+    template <class Progress>
+    friend void read_binary (std::istream& is, gpu_hashmap& m, part_id partId, Progress& progress) { m.deserialize(is, partId, progress); }
+    friend void write_binary (std::ostream&, gpu_hashmap&, part_id) { out_of_scope(); }
+
+    template <class Progress>
+    void deserialize (std::istream& is, part_id partId, Progress& progress) {
+        gpu_hashmap& m = *this;
         std::uint64_t hdr[3];
         is.read(reinterpret_cast<char*>(hdr), sizeof hdr);
         if (!is) throw std::runtime_error("could not read database part header");
@@ -146,19 +193,27 @@ public:
             if (!is) throw std::runtime_error("database part is truncated");
             if (mcb200_db_part_append(m.db_, partId, keys.data(), sizes.data(), vals.data(), b, nv)) throw_last("read_binary");
             done += b;
+            advance(progress, b, nkeys, done);
         }
         if (mcb200_db_part_finish(m.db_, partId)) throw_last("read_binary");
     }
 
     /** copy_target_lineages_to_gpus (gpu_hashmap.cuh): kept on the host for `tax` pointers;
      *  the device gets the per-target key at the rank given to query_async */
-    void copy_target_lineages_to_gpus (const std::vector<ranked_lineage>& lins) { lineages_ = lins; taxRank_ = -1; }
+    template <class Lineages>
+    void copy_target_lineages_to_gpus (const Lineages& lins) {
+        lineages_.resize(lins.size());
+        for (std::size_t t = 0; t < lins.size(); ++t)
+            for (std::size_t r = 0; r < 21 && r < lins[t].size(); ++r) lineages_[t][r] = lins[t][r];
+        taxRank_ = -1;
+    }
 
-    //--- the query entry point (gpu_hashmap.cu:1299-1313) ---
+    //--- the query entry point (gpu_hashmap.cu:1299-1313); Rank = taxon_rank / int ---
+    template <class Rank>
     void query_async (query_batch<ValueT>& batch, part_id hostId, const sketching_opt& sk,
-                      taxon_rank lowestRank) const;
+                      Rank lowestRank) const;
 
-    const void* taxon_of (target_id tgt, taxon_rank lowest) const noexcept {
+    tax_pointer taxon_of (target_id tgt, int lowest) const noexcept {
         if (tgt >= lineages_.size()) return nullptr;
         for (int r = lowest; r < 21; ++r) if (lineages_[tgt][r]) return lineages_[tgt][r];   // taxonomy.hpp:1260-1267
         return nullptr;
@@ -170,6 +225,14 @@ public:
     feature_count_type bucket_count () const noexcept { return sum(&mcb200_db_bucket_count); }
     feature_count_type dead_feature_count () const noexcept { return 0; }
     bool empty () const noexcept { return key_count() == 0; }
+    /** not supported by the reference's GPU store either (gpu_hashmap.cuh:186-200, 226-234) */
+    template <class... A> feature_count_type remove_features_with_more_locations_than (A&&...) { return 0; }
+    template <class... A> feature_count_type remove_ambiguous_features (A&&...) { return 0; }
+    void print_feature_map (std::ostream&) const {}
+    void print_feature_counts (std::ostream&) const {}
+#ifdef MCB200_IN_REFERENCE_TREE
+    mc::statistics_accumulator location_list_size_statistics () const { return mc::statistics_accumulator{}; }
+#endif
     static bucket_size_type max_supported_locations_per_feature () noexcept { return bucket_size_type(mcb200_max_supported_locations_per_feature()); }
     void max_locations_per_feature (bucket_size_type n) { maxLoc_ = n < 1 ? 1 : (n > 254 ? 254 : n); }
     bucket_size_type max_locations_per_feature () const noexcept { return maxLoc_; }
@@ -180,7 +243,7 @@ public:
 
     //--- build side: out of scope ---
     void initialize_tables (part_id) { out_of_scope(); }
-    template <class Seq> window_id add_target (part_id, const Seq&, target_id, const sketching_opt&) { out_of_scope(); return 0; }
+    template <class... A> window_id add_target (A&&...) { out_of_scope(); return 0; }
     void wait_until_add_target_complete (part_id, const sketching_opt&) {}
     bool add_target_failed (part_id) const noexcept { return false; }
     bool check_load_factor (part_id) const noexcept { return true; }
@@ -195,13 +258,18 @@ private:
         return s;
     }
     [[noreturn]] static void out_of_scope () { throw std::logic_error("libmcb200 implements the query path only"); }
+    static void advance (int&, std::uint64_t, std::uint64_t, std::uint64_t) {}
+    template <class P> static auto advance (P& p, std::uint64_t, std::uint64_t total, std::uint64_t done) -> decltype(p.counter, void()) {
+        // concurrent_progress counts bytes of the part file (database.cpp:140-165); we report the fraction of keys
+        if (total && std::size_t(p.total) > 0) p.counter = std::size_t(double(p.total) * double(done) / double(total));
+    }
 
     int device_;
     mcb200_db* db_ = nullptr;
     float maxLoadFactor_ = 0.f;
     bucket_size_type maxLoc_ = 254;
     std::vector<ranked_lineage> lineages_;
-    mutable taxon_rank taxRank_ = 0;     // rank whose keys are on the device (0 = sequence: none needed)
+    mutable int taxRank_ = 0;            // rank whose keys are on the device (0 = sequence: none needed)
     friend class query_batch<ValueT>;
 };
 
@@ -211,9 +279,10 @@ template <class Location = location>
 class query_batch
 {
 public:
-    using index_type    = std::uint32_t;
-    using size_type     = std::uint32_t;
-    using location_type = Location;
+    using index_type      = std::uint32_t;
+    using size_type       = std::uint32_t;
+    using location_type   = Location;
+    using match_locations = std::vector<location_type>;      // query_batch.cuh:57
 
     /** query_batch.cuh:60-259 */
     class query_host_data {
@@ -230,18 +299,18 @@ public:
                 for (size_type i = 0; i < maxCand_; ++i) {
                     match_candidate& m = cands_[std::size_t(q) * maxCand_ + i];
                     m.tgt = c[i].tgt; m.hits = c[i].hits; m.pos.beg = c[i].beg; m.pos.end = c[i].end;
-                    m.tax = (c[i].hits && store_) ? store_->taxon_of(c[i].tgt, lowest_) : nullptr;
+                    m.tax = (c[i].hits && store_) ? store_->taxon_of(c[i].tgt, lowest_) : tax_pointer(nullptr);
                 }
             }
         }
         span<location_type> allhits (index_type id) const noexcept {
             std::uint64_t n = 0;
             const std::uint64_t* p = mcb200_batch_allhits(b_, slot_, id, &n);
-            return span<location_type>{reinterpret_cast<const location_type*>(p), std::size_t(n)};
+            return make_span(reinterpret_cast<const location_type*>(p), std::size_t(n));
         }
         span<match_candidate> top_candidates (index_type id) const noexcept {
-            if (id >= num_queries() || cands_.empty()) return {};
-            return span<match_candidate>{cands_.data() + std::size_t(id) * maxCand_, maxCand_};
+            if (id >= num_queries() || cands_.empty()) return span<match_candidate>{};
+            return make_span(static_cast<const match_candidate*>(cands_.data()) + std::size_t(id) * maxCand_, std::size_t(maxCand_));
         }
         void clear () noexcept { mcb200_batch_clear(b_, slot_); numWindows_ = 0; }
         void lowest_rank (int r) noexcept { lowest_ = r; }
@@ -271,6 +340,7 @@ public:
         }
     }
     query_batch (const query_batch&) = delete;
+    query_batch (query_batch&& o) noexcept : b_(o.b_), numGPUs_(o.numGPUs_), host_(std::move(o.host_)) { o.b_ = nullptr; }
     ~query_batch () { if (b_) mcb200_batch_destroy(b_); }
 
     part_id gpu_count () const noexcept { return numGPUs_; }
@@ -302,9 +372,11 @@ private:
 };
 
 template <class Key, class ValueT>
+template <class Rank>
 void gpu_hashmap<Key, ValueT>::query_async (query_batch<ValueT>& batch, part_id hostId,
-                                            const sketching_opt& sk, taxon_rank lowestRank) const
+                                            const sketching_opt& sk, Rank lowestRankIn) const
 {
+    const int lowestRank = int(lowestRankIn);
     // `-lowest` above sequence: per-target taxon keys at that rank (candidate_generation.hpp:184-191)
     if (lowestRank != taxRank_) {
         if (lowestRank <= 0) { if (mcb200_db_set_target_taxa(db_, nullptr, 0)) throw_last("query_async"); }
@@ -317,7 +389,7 @@ void gpu_hashmap<Key, ValueT>::query_async (query_batch<ValueT>& batch, part_id 
         taxRank_ = lowestRank;
     }
     batch.host_data(hostId).lowest_rank(lowestRank);
-    const mcb200_sketching s{sk.kmerlen, sk.sketchlen, sk.winlen, sk.winstride};
+    const mcb200_sketching s{std::uint32_t(sk.kmerlen), std::uint32_t(sk.sketchlen), std::uint32_t(sk.winlen), std::uint32_t(sk.winstride)};
     if (mcb200_batch_submit(batch.handle(), hostId, &s)) throw_last("query_async");
 }
 

@@ -88,7 +88,7 @@ class NumpyBackend:
             cat = np.concatenate([lists[int(i)] for i in data[:n]])
             locs[:len(cat)] = torch.from_numpy(cat.astype(np.uint64).view(np.int64))
 
-    def reduce(self, slot, pos, runs, max_win, nq, top):
+    def reduce(self, slot, pos, runs, max_win, nq, top, mean_locations=0.0):
         pos = pos.numpy().astype(np.int64)
         out = top.numpy().view(np.uint32)
         out[:, :, 0] = 0xFFFFFFFF
