@@ -279,7 +279,7 @@ def host_sample(flat, offs, n):
 
 def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, device):
     """End to end through the query_batch seam, from the CALLER'S host buffers to candidates in host
-    memory: worker threads (one per host core, two slots each, as the reference's query workers own one
+    memory: worker threads (one per host core, three slots each, as the reference's query workers own one
     query_batch host slot each, database_query.hpp:87-124) add their share of the reads - which packs
     the bases to 2 bits + ambiguity bit into the slot's pinned buffers -, submit (H2D + kernels + D2H on
     the slot's stream) and wait.  Timed by wall clock over K back-to-back steps, host work included."""
@@ -289,7 +289,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     T = max(1, min(os.cpu_count() or 1, args.e2e_threads or 32))
     per = min(args.slot_reads, (nq + T - 1) // T)
     chunks = [(c, min(c + per, nq)) for c in range(0, nq, per)]
-    nslots = 2 * T
+    nslots = 3 * T
     slot_bases = max(int(host_offs[e] - host_offs[b]) for b, e in chunks)
     qb = _lib.check_ptr(L.mcb200_batch_create(db._h, per, slot_bases + 64, MAXC, 0, nslots))
     tops = np.zeros((nq, MAXC, 4), np.uint32)
@@ -300,24 +300,31 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     errors = []
     spent = [[0.0, 0.0, 0.0] for _ in range(T)]               # per worker: wait + collect | add (pack) | submit
 
+    SPW = 3                                                    # slots per worker: fill one while two are in flight
+    verify_n = min(len(top_first), nq) if top_first is not None else 0
+
     def collect(slot, ci):
+        """wait: the candidates of the chunk are then in the slot's pinned host buffer (the D2H copy is part of
+        the submit); they are copied out only where they are compared with the device-resident path"""
         _lib.check(L.mcb200_batch_wait(qb, slot))
         b, e = chunks[ci]
-        src = L.mcb200_batch_top_candidates(qb, slot, 0)
-        C.memmove(tops[b:e].ctypes.data, src, (e - b) * MAXC * 16)
+        if b < verify_n:
+            src = L.mcb200_batch_top_candidates(qb, slot, 0)
+            C.memmove(tops[b:e].ctypes.data, src, (e - b) * MAXC * 16)
 
     def worker(t, steps, start):
         try:
             mine = list(range(t, len(chunks), T))
-            pending = [None, None]
+            pending = [None] * SPW
             k = 0
             start.wait()
             for _ in range(steps):
                 for ci in mine:
-                    slot = 2 * t + (k & 1)
+                    j = k % SPW
+                    slot = SPW * t + j
                     t0 = time.perf_counter()
-                    if pending[k & 1] is not None:
-                        collect(slot, pending[k & 1])
+                    if pending[j] is not None:
+                        collect(slot, pending[j])
                     _lib.check(L.mcb200_batch_clear(qb, slot))
                     t1 = time.perf_counter()
                     b, e = chunks[ci]
@@ -328,12 +335,13 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                     _lib.check(L.mcb200_batch_submit(qb, slot, C.byref(sk)))
                     t3 = time.perf_counter()
                     spent[t][0] += t1 - t0; spent[t][1] += t2 - t1; spent[t][2] += t3 - t2
-                    pending[k & 1] = ci
+                    pending[j] = ci
                     k += 1
             t0 = time.perf_counter()
-            for j in (0, 1):
-                if pending[(k + j) & 1] is not None:
-                    collect(2 * t + ((k + j) & 1), pending[(k + j) & 1])
+            for i in range(SPW):
+                j = (k + i) % SPW
+                if pending[j] is not None:
+                    collect(SPW * t + j, pending[j])
             spent[t][0] += time.perf_counter() - t0
         except Exception as ex:                                   # surfaced by the caller
             errors.append(ex)
@@ -362,7 +370,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                for i, k_ in enumerate(("wait_results", "add_reads_pack", "submit"))}
     same = None
     if top_first is not None:
-        n = min(len(top_first), nq)
+        n = verify_n
         same = bool(np.array_equal(tops[:n], np.ascontiguousarray(top_first[:n]).view(np.uint32).reshape(n, MAXC, 4)))
 
     # the same slots already filled (no host packing in the timed region): H2D + kernels + D2H only,

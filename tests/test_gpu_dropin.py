@@ -19,6 +19,13 @@ COMMON = ("-no-query-params -mapped-only -precision -ground-truth -tophits -allh
           "-abundances -abundance-per species -threads {threads}")
 
 
+def _six_digits(line):
+    """The golden file predates printing.cpp:458 (`setprecision(15)` for fractional abundances): the
+    unmodified CPU reference built from the same sources prints 17.7777777777778 where the file has
+    17.7778 (14 lines).  Both sides are compared at the stream default of 6 significant digits."""
+    return re.sub(r"\d+\.\d{7,}", lambda m: "%g" % float(m.group(0)), line)
+
+
 def _filter(text):
     """run_tests:153: grep "|\\|#" | grep -v "time\\|speed\\|list\\|ignore" | sed "s/\\.fa//g" """
     out = []
@@ -27,7 +34,7 @@ def _filter(text):
             continue
         if re.search(r"time|speed|list|ignore", line):
             continue
-        out.append(line.replace(".fa", ""))
+        out.append(_six_digits(line.replace(".fa", "")))
     return out
 
 
