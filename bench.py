@@ -54,10 +54,11 @@ def parse():
     ap.add_argument("--replicate", action="store_true",
                     help="N > 1: every GPU holds the SAME single-part database and queries only its own reads "
                          "(the reference's -replicate mode, SURVEY 8e) instead of the target-sharded database")
-    ap.add_argument("--shard-by", default="feature", choices=["feature", "target"],
-                    help="N > 1: feature = every GPU owns a slice of the FEATURE space with the locations of all parts "
-                         "(one table access per feature however many GPUs; default); target = the reference's own "
-                         "partitioning, every GPU probes every read against its part (capacity mode / parity oracle)")
+    ap.add_argument("--shard-by", default="target", choices=["feature", "target"],
+                    help="N > 1: target = the reference's own partitioning, one part per GPU, every GPU probes every read "
+                         "against its part (default: the faster mode on DB-S at every N measured); feature = every GPU owns "
+                         "a slice of the FEATURE space with the locations of all parts (one table access per feature "
+                         "however many GPUs; location lists travel back to the read's GPU)")
     ap.add_argument("--shard-streams", type=int, default=3, help="CUDA streams of the feature-sharded chunk pipeline (1 = every operation serial, for profiling)")
     ap.add_argument("--chunk-reads", type=int, default=1_250_000, help="reads per pipeline chunk of the feature-sharded step")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")

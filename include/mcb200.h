@@ -79,6 +79,16 @@ int          mcb200_device_count (void);
 /* prepare_query_tables(numParts, replication) (gpu_hashmap.cu:1320-1362):
  * a store with n_parts read-only tables resident on CUDA device `device`.    */
 mcb200_db*   mcb200_db_open  (int device, uint32_t n_parts);
+/* the same store over several devices of ONE process (gpu_hashmap::config_gpu_count /
+ * prepare_query_tables, gpu_hashmap.cuh:116-130, gpu_hashmap.cu:1320-1362: one part
+ * per GPU): part p is resident on CUDA device devices[p].  devices[0] is the home
+ * device: batches are copied there and sketched there, every other device receives
+ * the sketches over the peer link, queries its parts on its own stream and returns
+ * their candidates, the home device merges in part order - instead of the
+ * reference's chain, in which every GPU forwards the whole batch to the next one
+ * (gpu_hashmap.cu:1255-1292, query_batch.cu:464-527).  All entry points below take
+ * such a store; all-hits output and feature shards need a single-device store.   */
+mcb200_db*   mcb200_db_open_multi (uint32_t n_parts, const int* devices);
 void         mcb200_db_close (mcb200_db* db);
 
 /* read_binary(istream&, store&, part_id, progress) (gpu_hashmap.cu:813-912):
@@ -119,7 +129,8 @@ uint64_t mcb200_db_key_count    (const mcb200_db* db, uint32_t part); /* key_cou
 uint64_t mcb200_db_value_count  (const mcb200_db* db, uint32_t part); /* value_count()  */
 uint64_t mcb200_db_bucket_count (const mcb200_db* db, uint32_t part); /* bucket_count() = slots */
 uint64_t mcb200_db_device_bytes (const mcb200_db* db, uint32_t part);
-int      mcb200_db_device       (const mcb200_db* db);
+int      mcb200_db_device       (const mcb200_db* db);                /* home device */
+int      mcb200_db_part_device  (const mcb200_db* db, uint32_t part);
 /* max_supported_locations_per_feature() (gpu_hashmap.cuh): 254 */
 uint32_t mcb200_max_supported_locations_per_feature (void);
 

@@ -85,6 +85,8 @@ _SIGS = {
     "mcb200_reader_skip": (C.c_int64, [_P, C.c_uint64, _P]),
     "mcb200_reader_fill_batch": (C.c_int64, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P]),
     "mcb200_db_open": (_P, [C.c_int, C.c_uint32]),
+    "mcb200_db_open_multi": (_P, [C.c_uint32, C.POINTER(C.c_int)]),
+    "mcb200_db_part_device": (C.c_int, [_P, C.c_uint32]),
     "mcb200_db_close": (None, [_P]),
     "mcb200_db_part_begin": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float]),
     "mcb200_db_part_append": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint64]),

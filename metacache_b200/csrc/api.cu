@@ -111,7 +111,24 @@ struct mcb200_db {
     // staging for host appends
     DevBuf<uint32_t> st_keys; DevBuf<uint8_t> st_sizes; DevBuf<uint64_t> st_off;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+    // multi-device store (mcb200_db_open_multi): this object is only the directory; every device holds
+    // an ordinary single-device store with the parts resident there.  children[0] is the home device
+    // (sketching, merge, results); part p is children[part_map[p].first]'s part part_map[p].second.
+    std::vector<mcb200_db*> children;
+    std::vector<std::pair<uint32_t, uint32_t>> part_map;
 };
+
+// part-level entry points of a multi-device store forward to the store that holds the part
+#define FORWARD_PART(db, part, call) \
+    if ((db) && !(db)->children.empty()) { \
+        if ((part) >= (db)->part_map.size()) return fail(MCB200_EINVAL, "part %u out of range (%zu parts)", unsigned(part), (db)->part_map.size()); \
+        mcb200_db* c_ = (db)->children[(db)->part_map[part].first]; const uint32_t lp_ = (db)->part_map[part].second; \
+        (void)c_; (void)lp_; return call; }
+#define FORWARD_PART_VALUE(db, part, call) \
+    if ((db) && !(db)->children.empty()) { \
+        if ((part) >= (db)->part_map.size()) return 0; \
+        const mcb200_db* c_ = (db)->children[(db)->part_map[part].first]; const uint32_t lp_ = (db)->part_map[part].second; \
+        return call; }
 
 // for the host-only translation units of the library (reader.cpp)
 extern "C" int mcb200_internal_set_error (int code, const char* msg) { return fail(code, "%s", msg ? msg : ""); }
@@ -162,6 +179,40 @@ extern "C" mcb200_db* mcb200_db_open (int device, uint32_t n_parts) {
     return db;
 }
 
+extern "C" mcb200_db* mcb200_db_open_multi (uint32_t n_parts, const int* devices) {
+    if (n_parts == 0 || !devices) { fail(MCB200_EINVAL, "n_parts must be >= 1 and devices non-null"); return nullptr; }
+    std::vector<int> distinct;
+    std::vector<uint32_t> count;
+    std::vector<std::pair<uint32_t, uint32_t>> map(n_parts);
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        size_t k = 0;
+        while (k < distinct.size() && distinct[k] != devices[p]) ++k;
+        if (k == distinct.size()) { distinct.push_back(devices[p]); count.push_back(0); }
+        map[p] = {uint32_t(k), count[k]++};
+    }
+    if (distinct.size() == 1) return mcb200_db_open(distinct[0], n_parts);
+    mcb200_db* db = new (std::nothrow) mcb200_db;
+    if (!db) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
+    for (size_t k = 0; k < distinct.size(); ++k) {
+        mcb200_db* c = mcb200_db_open(distinct[k], count[k]);
+        if (!c) { mcb200_db_close(db); return nullptr; }
+        db->children.push_back(c);
+    }
+    // the home device reads results from / writes sketches to the others
+    for (size_t k = 1; k < distinct.size(); ++k) {
+        int ok01 = 0, ok10 = 0;
+        cudaDeviceCanAccessPeer(&ok01, distinct[0], distinct[k]);
+        cudaDeviceCanAccessPeer(&ok10, distinct[k], distinct[0]);
+        if (ok01) { cudaSetDevice(distinct[0]); if (cudaDeviceEnablePeerAccess(distinct[k], 0) != cudaSuccess) cudaGetLastError(); }
+        if (ok10) { cudaSetDevice(distinct[k]); if (cudaDeviceEnablePeerAccess(distinct[0], 0) != cudaSuccess) cudaGetLastError(); }
+    }
+    cudaSetDevice(distinct[0]);
+    db->device = distinct[0];
+    db->sm_count = db->children[0]->sm_count;
+    db->part_map = map;
+    return db;
+}
+
 static void free_chunks (Part& p) {
     for (auto& c : p.shard_chunks) { if (c.keys) cudaFree(c.keys); if (c.sizes) cudaFree(c.sizes); if (c.values) cudaFree(c.values); }
     p.shard_chunks.clear();
@@ -178,6 +229,11 @@ static void free_part (Part& p) {
 
 extern "C" void mcb200_db_close (mcb200_db* db) {
     if (!db) return;
+    if (!db->children.empty()) {
+        for (auto* c : db->children) mcb200_db_close(c);
+        delete db;
+        return;
+    }
     cudaSetDevice(db->device);
     for (auto& p : db->parts) free_part(p);
     if (db->d_tax) cudaFree(db->d_tax);
@@ -198,6 +254,7 @@ static int part_begin_impl (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64
 
 extern "C" int mcb200_db_part_begin (mcb200_db* db, uint32_t part, uint64_t nkeys, uint64_t nvalues,
                                      float max_load_factor) {
+    FORWARD_PART(db, part, mcb200_db_part_begin(c_, lp_, nkeys, nvalues, max_load_factor));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (p.shard_mode) { p.begun = true; ++p.src_part; return 0; }   // next source part of a sharded load
@@ -280,6 +337,7 @@ static int shard_collect (mcb200_db* db, Part& p, const uint32_t* d_keys, const 
 extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,
                                       const uint8_t* sizes, const uint64_t* values,
                                       uint64_t nkeys, uint64_t nvalues) {
+    FORWARD_PART(db, part, mcb200_db_part_append(c_, lp_, keys, sizes, values, nkeys, nvalues));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
@@ -310,6 +368,7 @@ extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32
 extern "C" int mcb200_db_part_append_device (mcb200_db* db, uint32_t part, const uint32_t* d_keys,
                                              const uint8_t* d_sizes, const uint64_t* d_values,
                                              uint64_t nkeys, uint64_t nvalues) {
+    FORWARD_PART(db, part, mcb200_db_part_append_device(c_, lp_, d_keys, d_sizes, d_values, nkeys, nvalues));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
@@ -325,6 +384,7 @@ extern "C" int mcb200_db_part_append_device (mcb200_db* db, uint32_t part, const
 }
 
 extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
+    FORWARD_PART(db, part, mcb200_db_part_finish(c_, lp_));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.begun) return fail(MCB200_ESTATE, "part %u: finish without begin", part);
@@ -348,6 +408,7 @@ extern "C" int mcb200_db_part_finish (mcb200_db* db, uint32_t part) {
 
 extern "C" int mcb200_db_shard_begin (mcb200_db* db, uint32_t part, uint32_t shard, uint32_t n_shards,
                                       uint32_t n_targets) {
+    FORWARD_PART(db, part, fail(MCB200_EINVAL, "feature shards live on single-device stores (one process per GPU)"));
     CHECK_DB(db, part);
     if (n_shards == 0 || n_shards > 32 || shard >= n_shards) return fail(MCB200_EINVAL, "shard %u of %u unsupported (1..32 shards)", shard, n_shards);
     Part& p = db->parts[part];
@@ -364,6 +425,7 @@ extern "C" int mcb200_db_shard_begin (mcb200_db* db, uint32_t part, uint32_t sha
 
 extern "C" int mcb200_db_shard_finish (mcb200_db* db, uint32_t part, float max_load_factor,
                                        uint32_t max_target_id, uint32_t max_window_id) {
+    FORWARD_PART(db, part, fail(MCB200_EINVAL, "feature shards live on single-device stores (one process per GPU)"));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.shard_mode) return fail(MCB200_ESTATE, "part %u: mcb200_db_shard_begin must be called first", part);
@@ -461,6 +523,7 @@ extern "C" int mcb200_db_shard_finish (mcb200_db* db, uint32_t part, float max_l
 }
 
 extern "C" int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* max_target_id, uint32_t* max_window_id) {
+    FORWARD_PART(db, part, fail(MCB200_EINVAL, "feature shards live on single-device stores (one process per GPU)"));
     CHECK_DB(db, part);
     Part& p = db->parts[part];
     if (!p.shard_mode || !max_target_id || !max_window_id) return fail(MCB200_ESTATE, "part %u: not collecting a shard", part);
@@ -474,6 +537,7 @@ extern "C" int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* m
 
 extern "C" int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const char* path,
                                           float max_load_factor) {
+    FORWARD_PART(db, part, mcb200_db_load_cache_file(c_, lp_, path, max_load_factor));
     CHECK_DB(db, part);
     FILE* f = fopen(path, "rb");
     if (!f) return fail(MCB200_EIO, "cannot open '%s'", path);
@@ -503,6 +567,10 @@ extern "C" int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const ch
 
 extern "C" int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax, uint32_t n) {
     if (!db) return fail(MCB200_EINVAL, "null database handle");
+    if (!db->children.empty()) {
+        for (auto* c : db->children) { const int rc = mcb200_db_set_target_taxa(c, tax, n); if (rc) return rc; }
+        return 0;
+    }
     CU(cudaSetDevice(db->device));
     if (db->d_tax) { cudaFree(db->d_tax); db->d_tax = nullptr; db->n_tax = 0; }
     if (!tax || !n) return 0;
@@ -514,6 +582,7 @@ extern "C" int mcb200_db_set_target_taxa (mcb200_db* db, const uint64_t* tax, ui
 
 extern "C" int mcb200_db_set_target_lineages (mcb200_db* db, const uint32_t* lin, uint32_t n) {
     if (!db) return fail(MCB200_EINVAL, "null database handle");
+    if (!db->children.empty()) return mcb200_db_set_target_lineages(db->children[0], lin, n);     // classification runs at home
     CU(cudaSetDevice(db->device));
     if (db->d_lineages) { cudaFree(db->d_lineages); db->d_lineages = nullptr; db->n_lin = 0; }
     if (!lin || !n) return 0;
@@ -523,22 +592,35 @@ extern "C" int mcb200_db_set_target_lineages (mcb200_db* db, const uint32_t* lin
     return 0;
 }
 
-extern "C" uint32_t mcb200_db_part_count (const mcb200_db* db) { return db ? uint32_t(db->parts.size()) : 0; }
+extern "C" uint32_t mcb200_db_part_count (const mcb200_db* db) {
+    if (db && !db->children.empty()) return uint32_t(db->part_map.size());
+    return db ? uint32_t(db->parts.size()) : 0;
+}
 extern "C" uint64_t mcb200_db_key_count (const mcb200_db* db, uint32_t part) {
+    FORWARD_PART_VALUE(db, part, mcb200_db_key_count(c_, lp_));
     return (db && part < db->parts.size()) ? db->parts[part].keys_loaded : 0; }
 extern "C" uint64_t mcb200_db_value_count (const mcb200_db* db, uint32_t part) {
+    FORWARD_PART_VALUE(db, part, mcb200_db_value_count(c_, lp_));
     return (db && part < db->parts.size()) ? db->parts[part].values_loaded : 0; }
 extern "C" uint64_t mcb200_db_bucket_count (const mcb200_db* db, uint32_t part) {
+    FORWARD_PART_VALUE(db, part, mcb200_db_bucket_count(c_, lp_));
     return (db && part < db->parts.size()) ? db->parts[part].nbuckets * 2 : 0; }
 extern "C" uint64_t mcb200_db_device_bytes (const mcb200_db* db, uint32_t part) {
+    FORWARD_PART_VALUE(db, part, mcb200_db_device_bytes(c_, lp_));
     if (!db || part >= db->parts.size()) return 0;
     const Part& p = db->parts[part];
     return p.nbuckets * sizeof(Bucket) + (p.finished ? p.packed_bytes : (p.nvalues + 4) * 8);
 }
 extern "C" int mcb200_db_device (const mcb200_db* db) { return db ? db->device : -1; }
+extern "C" int mcb200_db_part_device (const mcb200_db* db, uint32_t part) {
+    if (!db) return -1;
+    if (db->children.empty()) return part < db->parts.size() ? db->device : -1;
+    return part < db->part_map.size() ? db->children[db->part_map[part].first]->device : -1;
+}
 
 extern "C" int mcb200_db_part_export (const mcb200_db* db, uint32_t part, uint32_t* keys,
                                       uint8_t* sizes, uint64_t* values) {
+    FORWARD_PART(db, part, mcb200_db_part_export(c_, lp_, keys, sizes, values));
     CHECK_DB(db, part);
     const Part& p = db->parts[part];
     if (!p.finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
@@ -566,6 +648,15 @@ struct mcb200_workspace {
     uint64_t scratch_entries = 0;
     DevBuf<int> error;
     DevBuf<ListArgs> lists;              // device copy of the runs handed to mcb200_shard_reduce_device
+    // multi-device store: `db` is the HOME store; parts on other devices are queried through one
+    // workspace per device (remote[k] lives on multi->children[k], k >= 1) on that device's own stream
+    mcb200_db* multi = nullptr;
+    std::vector<mcb200_workspace*> remote;
+    cudaEvent_t ev_sketched = nullptr;   // home: the sketches are complete
+    cudaStream_t own_stream = nullptr;   // remote: its stream, the event that ends its share of a call,
+    cudaEvent_t ev_done = nullptr;       //         and the buffers only a remote workspace needs
+    DevBuf<uint32_t> r_max_win; DevBuf<mcb200_candidate> r_top;
+    bool r_used = false;
     DevBuf<mcb200_candidate> part_tops;
     DevBuf<uint64_t> hit_counts, hit_offsets, allhits;
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
@@ -624,6 +715,27 @@ extern "C" mcb200_workspace* mcb200_workspace_create (mcb200_db* db, uint32_t ma
     if (max_candidates < 1 || max_candidates > 32) { fail(MCB200_EINVAL, "max_candidates %u unsupported (1..32)", max_candidates); return nullptr; }
     if (max_bases >= (1ull << 32) - 4096) { fail(MCB200_EINVAL, "max_bases must be < 4 Gi per workspace"); return nullptr; }
     if (max_seqs < max_queries) max_seqs = max_queries;
+    if (!db->children.empty()) {
+        if (want_all_hits) { fail(MCB200_EINVAL, "all-hits output needs a single-device store"); return nullptr; }
+        mcb200_workspace* home = mcb200_workspace_create(db->children[0], max_queries, max_seqs, max_bases, max_candidates, 0);
+        if (!home) return nullptr;
+        home->multi = db;
+        home->remote.assign(db->children.size(), nullptr);
+        cudaError_t e = cudaEventCreateWithFlags(&home->ev_sketched, cudaEventDisableTiming);
+        for (size_t k = 1; k < db->children.size() && e == cudaSuccess; ++k) {
+            mcb200_workspace* r = mcb200_workspace_create(db->children[k], max_queries, max_seqs, 64, max_candidates, 0);
+            if (!r) { mcb200_workspace_destroy(home); return nullptr; }
+            home->remote[k] = r;
+            e = cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming);
+        }
+        cudaSetDevice(db->device);
+        if (e != cudaSuccess) {
+            fail(MCB200_ECUDA, "multi-device workspace: %s", cudaGetErrorString(e));
+            mcb200_workspace_destroy(home); return nullptr;
+        }
+        return home;
+    }
     CUP(cudaSetDevice(db->device));
     mcb200_workspace* ws = new (std::nothrow) mcb200_workspace;
     if (!ws) { fail(MCB200_ENOMEM, "out of host memory"); return nullptr; }
@@ -650,7 +762,12 @@ extern "C" mcb200_workspace* mcb200_workspace_create (mcb200_db* db, uint32_t ma
 
 extern "C" void mcb200_workspace_destroy (mcb200_workspace* ws) {
     if (!ws) return;
+    for (auto* r : ws->remote) if (r) mcb200_workspace_destroy(r);
     cudaSetDevice(ws->db->device);
+    if (ws->own_stream) { cudaStreamSynchronize(ws->own_stream); cudaStreamDestroy(ws->own_stream); }
+    if (ws->ev_done) cudaEventDestroy(ws->ev_done);
+    if (ws->ev_sketched) cudaEventDestroy(ws->ev_sketched);
+    ws->r_max_win.release(); ws->r_top.release();
     ws->codes.release(); ws->amb.release(); ws->seq_nwin.release(); ws->seq_win_off.release();
     ws->win_seq.release(); ws->qry_win_off.release(); ws->feats.release(); ws->heavy_list.release();
     ws->heavy_count.release(); ws->counters.release(); ws->scratch_cursor.release();
@@ -740,6 +857,7 @@ static int sketch_impl (mcb200_workspace* ws, const mcb200_dev_queries* q, const
     launch_sketch(d_codes, d_amb, q->seq_offsets, ws->seq_win_off.p, ws->win_seq.p,
                   ws->seq_win_off.p + q->n_seqs, ws->sk, ws->feats.p, ws->db->sm_count, st);
     if (ws->profiling) { CU(cudaEventRecord(ws->ev->sk[3], st)); ws->ev->sketched = true; }
+    if (ws->multi) CU(cudaEventRecord(ws->ev_sketched, st));      // the other devices start from here
     CU(cudaGetLastError());
     ws->sketched = true;
     return 0;
@@ -792,10 +910,25 @@ static int check_overflow (mcb200_workspace* ws, cudaStream_t st) {
                 (unsigned long long)want, need);
 }
 
+// all devices of a multi-device workspace: EAGAIN if any of them grew its pool
+static int check_overflow_all (mcb200_workspace* ws, cudaStream_t st) {
+    int rc = check_overflow(ws, st);
+    if (rc && rc != MCB200_EAGAIN) return rc;
+    for (auto* r : ws->remote) {
+        if (!r || !r->r_used) continue;
+        cudaSetDevice(r->db->device);
+        const int rr = check_overflow(r, r->own_stream);
+        cudaSetDevice(ws->db->device);
+        if (rr && rr != MCB200_EAGAIN) return rr;
+        if (rr) rc = rr;
+    }
+    return rc;
+}
+
 extern "C" int mcb200_workspace_check (mcb200_workspace* ws) {
     if (!ws) return fail(MCB200_EINVAL, "null argument");
     CU(cudaSetDevice(ws->db->device));
-    return check_overflow(ws, ws->last_stream);
+    return check_overflow_all(ws, ws->last_stream);
 }
 
 static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top) {
@@ -833,16 +966,86 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
     return 0;
 }
 
+// A part on another device (multi-device store): its workspace receives the sketches over the peer
+// link, probes and reduces on its own stream, and sends the part's candidates back to the home device
+// (d_dst).  Replaces the reference's peer chain, gpu_hashmap.cu:1255-1292 / query_batch.cu:464-527,
+// where every GPU forwards the whole batch to the next one.  The caller makes `st` wait for r->ev_done.
+static int remote_query (mcb200_workspace* ws, uint32_t child, uint32_t local_part, mcb200_candidate* d_dst,
+                         cudaStream_t st) {
+    mcb200_workspace* r = ws->remote[child];
+    const int hdev = ws->db->device, rdev = r->db->device;
+    const uint32_t nq = ws->q.n_queries, s = ws->sk.s;
+    if (!r->db->parts[local_part].finished) return fail(MCB200_ESTATE, "a part on device %d is not loaded", rdev);
+    (void)st;
+    CU(cudaSetDevice(rdev));
+    int rc = 0;
+    cudaError_t e = cudaStreamWaitEvent(r->own_stream, ws->ev_sketched, 0);
+    const uint64_t nfeat = ws->win_bound * s;
+    if (e == cudaSuccess) e = r->feats.ensure(nfeat);
+    if (e == cudaSuccess) e = r->r_max_win.ensure(nq);
+    if (e == cudaSuccess) e = r->r_top.ensure(uint64_t(nq) * ws->maxc);
+    // (the window bound, not the window count, is known without a synchronisation)
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(r->feats.p, rdev, ws->feats.p, hdev, nfeat * 4, r->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(r->qry_win_off.p, rdev, ws->qry_win_off.p, hdev, (uint64_t(nq) + 1) * 4, r->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(r->r_max_win.p, rdev, ws->q.max_win, hdev, uint64_t(nq) * 4, r->own_stream);
+    if (e == cudaSuccess) {
+        r->warp_cap = ws->warp_cap;
+        rc = mcb200_query_sketches_device(r, local_part, r->feats.p, r->qry_win_off.p, r->r_max_win.p, nq, s, r->r_top.p,
+                                          r->own_stream);
+    }
+    if (e == cudaSuccess && !rc)
+        e = cudaMemcpyPeerAsync(d_dst, hdev, r->r_top.p, rdev, uint64_t(nq) * ws->maxc * sizeof(mcb200_candidate), r->own_stream);
+    if (e == cudaSuccess && !rc) e = cudaEventRecord(r->ev_done, r->own_stream);
+    r->r_used = true;
+    cudaSetDevice(hdev);
+    if (e != cudaSuccess) return fail(MCB200_ECUDA, "query on device %d failed: %s", rdev, cudaGetErrorString(e));
+    return rc;
+}
+
+static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
+                       const uint64_t* allhits_off, cudaStream_t st);
+
+// part index of the STORE the workspace was made for (the directory's numbering for a multi-device store)
+static int query_part_any (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_dst, const uint64_t* allhits_off,
+                           cudaStream_t st, bool* remote) {
+    if (remote) *remote = false;
+    if (!ws->multi) return query_part(ws, part, d_dst, allhits_off, st);
+    const auto m = ws->multi->part_map[part];
+    if (m.first == 0) return query_part(ws, m.second, d_dst, allhits_off, st);
+    if (remote) *remote = true;
+    return remote_query(ws, m.first, m.second, d_dst, st);
+}
+
+static uint32_t store_part_count (const mcb200_workspace* ws) {
+    return ws->multi ? uint32_t(ws->multi->part_map.size()) : uint32_t(ws->db->parts.size());
+}
+static bool store_part_loaded (const mcb200_workspace* ws, uint32_t part) {
+    if (part >= store_part_count(ws)) return false;
+    if (!ws->multi) return ws->db->parts[part].finished;
+    const auto m = ws->multi->part_map[part];
+    return ws->multi->children[m.first]->parts[m.second].finished;
+}
+// the home stream continues after the remote shares of the call
+static int join_remotes (mcb200_workspace* ws, cudaStream_t st) {
+    for (auto* r : ws->remote) if (r && r->r_used) CU(cudaStreamWaitEvent(st, r->ev_done, 0));
+    return 0;
+}
+
 extern "C" int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
                                          void* stream) {
     if (!ws || !d_top) return fail(MCB200_EINVAL, "null argument");
     if (!ws->sketched) return fail(MCB200_ESTATE, "mcb200_sketch_device must run first");
-    if (part >= ws->db->parts.size() || !ws->db->parts[part].finished)
-        return fail(MCB200_ESTATE, "part %u not loaded", part);
+    if (!store_part_loaded(ws, part)) return fail(MCB200_ESTATE, "part %u not loaded", part);
     CU(cudaSetDevice(ws->db->device));
     if (ws->q.n_queries == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ws->last_stream = st;
+    if (ws->multi) {
+        bool remote = false;
+        const int rc = query_part_any(ws, part, d_top, nullptr, st, &remote);
+        if (rc) return rc;
+        return remote ? join_remotes(ws, st) : 0;
+    }
     // asynchronous: a read that outgrows the scratch pool raises the sticky device flag 3 and gets
     // empty candidates; mcb200_workspace_check() reports it (and grows the pool) after the stream drained
     return query_part(ws, part, d_top, nullptr, st);
@@ -885,6 +1088,7 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
 // feature-space sharding: the three device steps around the two exchanges (kernels_shard.cu)
 // ---------------------------------------------------------------------------
 extern "C" uint32_t mcb200_db_location_bytes (const mcb200_db* db, uint32_t part) {
+    FORWARD_PART_VALUE(db, part, mcb200_db_location_bytes(c_, lp_));
     if (!db || part >= db->parts.size() || !db->parts[part].finished) return 0;
     return db->parts[part].win_bits ? 4u : 8u;
 }
@@ -1008,11 +1212,12 @@ static int query_device_impl (mcb200_workspace* ws, const mcb200_dev_queries* q,
                               const uint32_t* d_amb, const mcb200_sketching* sk, mcb200_candidate* d_top,
                               void* stream) {
     if (!ws || !q || !d_top) return fail(MCB200_EINVAL, "null argument");
-    for (auto& p : ws->db->parts) if (!p.finished) return fail(MCB200_ESTATE, "database part not loaded");
+    for (uint32_t p = 0; p < store_part_count(ws); ++p)
+        if (!store_part_loaded(ws, p)) return fail(MCB200_ESTATE, "database part not loaded");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = sketch_impl(ws, q, sk, stream, d_codes, d_amb);
     if (rc) return rc;
-    const uint32_t np = uint32_t(ws->db->parts.size());
+    const uint32_t np = store_part_count(ws);
     const uint32_t nq = q->n_queries;
     if (nq == 0) return 0;
 
@@ -1048,9 +1253,10 @@ static int query_device_impl (mcb200_workspace* ws, const mcb200_dev_queries* q,
                 count_launch();
                 poff = v;
             }
-            rc = query_part(ws, p, dst, poff, st);
+            rc = query_part_any(ws, p, dst, poff, st, nullptr);
             if (rc) return rc;
         }
+        if (ws->multi) { rc = join_remotes(ws, st); if (rc) return rc; }
         if (np > 1) {
             if (ws->profiling && ws->ev) CU(cudaEventRecord(ws->ev->merge[0], st));
             launch_merge_candidates(ws->part_tops.p, np, nq, ws->maxc, ws->db->d_tax, ws->db->n_tax, d_top, st);
@@ -1158,6 +1364,7 @@ extern "C" int mcb200_db_build_part_from_targets (mcb200_db* db, uint32_t part,
                                                   uint32_t n_targets, uint32_t first_target_id,
                                                   const mcb200_sketching* sk, uint32_t max_locations,
                                                   float max_load_factor, uint32_t* out_windows) {
+    FORWARD_PART(db, part, mcb200_db_build_part_from_targets(c_, lp_, d_bases, d_seq_offsets, n_targets, first_target_id, sk, max_locations, max_load_factor, out_windows));
     CHECK_DB(db, part);
     int rc = validate_sketching(sk);
     if (rc) return rc;
@@ -1480,7 +1687,7 @@ extern "C" int mcb200_batch_wait (mcb200_batch* b, uint32_t slot) {
         cudaEventElapsedTime(&s.kernels_ms, s.ev_k0, s.ev_k1);
         s.waited = true;
         if (s.n_queries) {
-            int rc = check_overflow(s.ws, s.stream);
+            int rc = check_overflow_all(s.ws, s.stream);
             if (rc == MCB200_EAGAIN) {
                 // a huge read outgrew its scratch region (pool grown by the check): redo this submit
                 const mcb200_sketching sk{s.ws->sk.k, s.ws->sk.s, s.ws->sk.w, s.ws->sk.stride};

@@ -483,70 +483,72 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     if (ok && H != 0) {
         // ---- hits of the window ranges ending at the (one or two) windows of every table entry;
         //      lane-local best and best of another target; order: (hits desc, location asc) ----
-        uint32_t c1 = 0, c2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
+        // `far` = distance from the end window of a range to its first occupied window: the candidate's
+        // window range is [end - far, end] (what the reference's scan keeps in `fst`), found with the
+        // same lookups as the sums
+        uint32_t c1 = 0, c2 = 0, f1 = 0, f2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
         for (uint32_t j = lane; j < D; j += 32) {
             const uint32_t slot = list[j];
             const K kb = hkeys[slot];
             const uint32_t cnt = hcnt[slot];
             const uint32_t n0 = cnt & 0xFFFFu, n1 = cnt >> 16;
             uint32_t h0 = n0, h1 = n1 + (W > 1 ? n0 : 0u);
+            uint32_t far0 = 0, far1 = (W > 1 && n0 != 0) ? 1u : 0u;
             const uint32_t pidx = AK::pair_index(kb, wb);
             // pair b-i holds the windows at distance 2i-1, 2i (from the even window) and 2i, 2i+1 (from the odd one)
             for (uint32_t i = 1; 2 * i - 1 < W && i <= pidx; ++i) {
                 const uint32_t x = agg_lookup<K>(hkeys, hcnt, mask, K(kb - i));
                 const uint32_t lo = x & 0xFFFFu, hi = x >> 16;
                 h0 += hi;
-                if (2 * i < W) { h0 += lo; h1 += hi; }
-                if (2 * i + 1 < W) h1 += lo;
+                if (hi) far0 = 2 * i - 1;
+                if (2 * i < W) { h0 += lo; h1 += hi; if (lo) far0 = 2 * i; if (hi) far1 = 2 * i; }
+                if (2 * i + 1 < W) { h1 += lo; if (lo) far1 = 2 * i + 1; }
             }
             // the entry's candidate: more hits, the even (smaller) window on ties; a window without locations ends no range
             const bool odd = (n1 != 0) && (n0 == 0 || h1 > h0);
-            const uint32_t c = odd ? h1 : h0;
+            const uint32_t c = odd ? h1 : h0, f = odd ? far1 : far0;
             const K k = K((kb << 1) | K(odd));
-            hits[j] = (c << 1) | uint32_t(odd);
+            hits[j] = (c << 4) | (f << 1) | uint32_t(odd);
             if (c > c1 || (c == c1 && k < k1)) {
-                if (c1 != 0 && AK::tgt(k1, wb) != AK::tgt(k, wb)) { c2 = c1; k2 = k1; }
-                c1 = c; k1 = k;
-            } else if (AK::tgt(k, wb) != AK::tgt(k1, wb) && (c > c2 || (c == c2 && k < k2))) { c2 = c; k2 = k; }
+                if (c1 != 0 && AK::tgt(k1, wb) != AK::tgt(k, wb)) { c2 = c1; k2 = k1; f2 = f1; }
+                c1 = c; k1 = k; f1 = f;
+            } else if (AK::tgt(k, wb) != AK::tgt(k1, wb) && (c > c2 || (c == c2 && k < k2))) { c2 = c; k2 = k; f2 = f; }
         }
         __syncwarp();
         // ---- top-k distinct targets ----------------------------------------------
         uint32_t c = 0, last = 0xFFFFFFFFu;
         for (; c < a.maxc; ++c) {
-            uint32_t best_c = c1; K best_k = k1;
+            uint32_t best_c = c1, best_f = f1; K best_k = k1;
             if (c == 1) {
                 // second round: a lane's best outside the winning target is its best, or its runner-up
-                if (c1 != 0 && AK::tgt(k1, wb) == last) { best_c = c2; best_k = k2; }
+                if (c1 != 0 && AK::tgt(k1, wb) == last) { best_c = c2; best_k = k2; best_f = f2; }
             } else if (c > 1) {
-                best_c = 0; best_k = AK::kEmpty;
+                best_c = 0; best_k = AK::kEmpty; best_f = 0;
                 for (uint32_t j = lane; j < D; j += 32) {
                     const uint32_t e = hits[j];
                     const K k = K((hkeys[list[j]] << 1) | K(e & 1u));
                     const uint32_t tgt = AK::tgt(k, wb);
                     bool taken = false;
                     for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
-                    const uint32_t cj = e >> 1;
-                    if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; }
+                    const uint32_t cj = e >> 4;
+                    if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; best_f = (e >> 1) & 7u; }
                 }
             }
             const uint32_t wmax = __reduce_max_sync(kFull, best_c);
             if (wmax == 0) break;
             const bool cand = (best_c == wmax);
-            // smallest key among the lanes holding the maximum: (tgt, win) lexicographic
-            const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
-            const uint32_t wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
-            const uint32_t ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
-            if (lane == 0) {
-                // first window of the winning range: smallest present window in (ww-W, ww]
-                K ke;
-                if (sizeof(K) == 4) ke = K((wt << wb) | ww); else ke = K((uint64_t(wt) << 32) | ww);
-                uint32_t beg = ww;
-                for (uint32_t d = 1; d < W && d <= ww; ++d) {
-                    const K kd = K(ke - d);
-                    if ((agg_lookup<K>(hkeys, hcnt, mask, K(kd >> 1)) >> (16u * (uint32_t(kd) & 1u))) & 0xFFFFu) beg = ww - d;
-                }
-                top[c] = mcb200_candidate{wt, wmax, beg, ww};
-                chosen[c] = wt;
+            // smallest location among the lanes holding the maximum: (tgt, win) lexicographic; every lane's
+            // location is a different table entry, so exactly one lane wins and writes the candidate
+            uint32_t wt, ww;
+            if (sizeof(K) == 4) {
+                const uint32_t wk = __reduce_min_sync(kFull, cand ? uint32_t(best_k) : 0xFFFFFFFFu);
+                wt = AK::tgt(K(wk), wb); ww = AK::win(K(wk), wb);
+                if (cand && uint32_t(best_k) == wk) { top[c] = mcb200_candidate{wt, wmax, ww - best_f, ww}; chosen[c] = wt; }
+            } else {
+                const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
+                wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
+                ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
+                if (cand && bt == wt && bw == ww) { top[c] = mcb200_candidate{wt, wmax, ww - best_f, ww}; chosen[c] = wt; }
             }
             last = wt;
             __syncwarp();

@@ -72,8 +72,16 @@ class MatchCandidate:
 class Database:
     """Query half of mc::database with feature_store = the B200 table (database.hpp:183-189)."""
 
-    def __init__(self, device: int = 0, n_parts: int = 1):
-        self._h = check_ptr(lib().mcb200_db_open(device, n_parts))
+    def __init__(self, device: int = 0, n_parts: int = 1, devices: Optional[Sequence[int]] = None):
+        """devices: one CUDA device per part (mcb200_db_open_multi: a store over several GPUs of this
+        process, devices[0] = home device); default: all parts on `device`"""
+        if devices is not None:
+            import ctypes
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            self._h = check_ptr(lib().mcb200_db_open_multi(len(devices), arr))
+            device = int(devices[0])
+        else:
+            self._h = check_ptr(lib().mcb200_db_open(device, n_parts))
         self.device = device
         self.meta: Optional[DbMeta] = None
         self._lowest_rank = RANK_SEQUENCE

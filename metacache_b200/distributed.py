@@ -35,7 +35,10 @@ def _as_tensor(ptr, n, device):
 
 
 class ShardedQuery:
-    """Fixed-shape sharded query step: every rank contributes `nq` queries with `nwin` windows."""
+    """Target-sharded query step (the reference's partitioning): every rank contributes `nq` queries with
+    at most `nwin` windows (a capacity: reads of any length fit as long as the rank's window count stays
+    below it - the window bound n_bases / winstride + 2 * n_seqs always does; the receivers only read the
+    windows the gathered per-read window offsets name)."""
 
     def __init__(self, db, ws, nq: int, nwin: int, sketchlen: int, max_candidates: int, device, stream,
                  group=None):
@@ -44,6 +47,7 @@ class ShardedQuery:
         self.dist, self.torch = dist, torch
         self.db, self.ws, self.nq, self.nwin, self.S, self.k = db, ws, nq, nwin, sketchlen, max_candidates
         self.device, self.stream, self.group = device, stream, group
+        self.comm_stream = torch.cuda.Stream(device)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         w = self.world
@@ -60,13 +64,25 @@ class ShardedQuery:
         final candidates of THIS rank's slice."""
         L, dist, torch = _lib.lib(), self.dist, self.torch
         _lib.check(L.mcb200_sketch_device(self.ws, C.byref(q), C.byref(sk), self.sp))
-        mine_f = _as_tensor(L.mcb200_workspace_sketches(self.ws), self.nwin * self.S, self.device)
-        mine_w = _as_tensor(L.mcb200_workspace_query_windows(self.ws), self.nq + 1, self.device)
-        with torch.cuda.stream(self.stream):
+        f_ptr, w_ptr = L.mcb200_workspace_sketches(self.ws), L.mcb200_workspace_query_windows(self.ws)
+        mine_f = _as_tensor(f_ptr, self.nwin * self.S, self.device)
+        mine_w = _as_tensor(w_ptr, self.nq + 1, self.device)
+        sketched = torch.cuda.Event()
+        sketched.record(self.stream)
+        # the gathers run on their own stream while this rank probes ITS reads straight from the workspace
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(sketched)
             dist.all_gather_into_tensor(self.feats_all, mine_f, group=self.group)
             dist.all_gather_into_tensor(self.qwo_all, mine_w, group=self.group)
             dist.all_gather_into_tensor(self.maxwin_all, max_win, group=self.group)
+            gathered = torch.cuda.Event()
+            gathered.record(self.comm_stream)
+        _lib.check(L.mcb200_query_sketches_device(
+            self.ws, 0, f_ptr, w_ptr, max_win.data_ptr(), self.nq, self.S, self.send[self.rank].data_ptr(), self.sp))
+        self.stream.wait_event(gathered)
         for j in range(self.world):
+            if j == self.rank:
+                continue
             _lib.check(L.mcb200_query_sketches_device(
                 self.ws, 0, self.feats_all[j].data_ptr(), self.qwo_all[j].data_ptr(),
                 self.maxwin_all[j].data_ptr(), self.nq, self.S, self.send[j].data_ptr(), self.sp))

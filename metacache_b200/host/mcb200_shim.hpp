@@ -154,12 +154,29 @@ public:
     //--- query tables (gpu_hashmap.cu:1320-1362) ---
     void prepare_query_tables (part_id numParts, unsigned /*replication*/ = 1) {
         if (db_) mcb200_db_close(db_);
-        db_ = mcb200_db_open(device_, numParts);
+        // one part per GPU like the reference (gpu_hashmap.cuh:116-130) when the box has enough devices;
+        // MCB200_DEVICES="0,1,.." names the device of every part explicitly (cycled), a single entry = one GPU
+        std::vector<int> devs;
+        if (const char* e = std::getenv("MCB200_DEVICES")) {
+            std::vector<int> list;
+            for (const char* c = e; *c; ) { list.push_back(std::atoi(c)); while (*c && *c != ',') ++c; if (*c == ',') ++c; }
+            for (part_id p = 0; p < numParts && !list.empty(); ++p) devs.push_back(list[p % list.size()]);
+        } else if (numParts > 1 && part_id(mcb200_device_count()) >= numParts) {
+            for (part_id p = 0; p < numParts; ++p) devs.push_back(int(p));
+        }
+        db_ = devs.empty() ? mcb200_db_open(device_, numParts) : mcb200_db_open_multi(numParts, devs.data());
         if (!db_) throw_last("prepare_query_tables");
         current() = this;
     }
     part_id table_count () const noexcept { return db_ ? part_id(mcb200_db_part_count(db_)) : 0; }
-    part_id gpu_count () const noexcept { return 1; }
+    part_id gpu_count () const noexcept {
+        std::vector<int> seen;
+        for (part_id p = 0; db_ && p < table_count(); ++p) {
+            const int d = mcb200_db_part_device(db_, p);
+            if (std::find(seen.begin(), seen.end(), d) == seen.end()) seen.push_back(d);
+        }
+        return part_id(seen.empty() ? 1 : seen.size());
+    }
     void enable_peer_access () {}     // one process per GPU: no peer chain (gpu_hashmap.cu:1403-1420)
     void pop_status () {}
     void pop_status (part_id) {}

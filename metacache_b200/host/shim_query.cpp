@@ -3,7 +3,9 @@
  * written against mcb200_shim.hpp, to show (and test) that the shims carry the
  * reference's call sequence unchanged:
  *
- *   usage: shim_query <db.cacheN> <reads.txt> [maxcand] [copyAllHits]
+ *   usage: shim_query <db.cacheN | db> <reads.txt> [maxcand] [copyAllHits]
+ *          (<db> = base name of a multi-part database: db.cache0, db.cache1, ...; with several GPUs
+ *           prepare_query_tables puts one part on each, in this one process)
  *   reads.txt: one query per line, "SEQ1" or "SEQ1 SEQ2", "-" = empty
  *   output   : one line per query: id TAB tgt:hits:beg:end,... TAB nallhits
  ******************************************************************************/
@@ -23,10 +25,17 @@ int main (int argc, char** argv)
     const bool allhits = argc > 4 && std::stoi(argv[4]) != 0;
     try {
         gpu_hashmap<feature, location> store;                       // database::featureStore_
-        store.prepare_query_tables(1, 1);
-        std::ifstream is(argv[1], std::ios::binary);
-        if (!is) { std::cerr << "cannot open " << argv[1] << "\n"; return 1; }
-        read_binary(is, store, 0);                                  // database::read_cache
+        std::vector<std::string> files;
+        if (std::ifstream(argv[1], std::ios::binary)) files.push_back(argv[1]);
+        else for (int p = 0; std::ifstream(std::string(argv[1]) + ".cache" + std::to_string(p), std::ios::binary); ++p)
+            files.push_back(std::string(argv[1]) + ".cache" + std::to_string(p));
+        if (files.empty()) { std::cerr << "cannot open " << argv[1] << "\n"; return 1; }
+        store.prepare_query_tables(part_id(files.size()), 1);       // database::read (database.cpp:183-242)
+        for (std::size_t p = 0; p < files.size(); ++p) {
+            std::ifstream is(files[p], std::ios::binary);
+            read_binary(is, store, part_id(p));                     // database::read_cache
+        }
+        std::printf("# parts=%u devices=%u\n", unsigned(store.table_count()), unsigned(store.gpu_count()));
 
         const sketching_opt sk;                                     // db.target_sketching()
         const std::size_t batchSize = 8192;                         // options.hpp:228
