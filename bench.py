@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--e2e-threads", type=int, default=0, help="host worker threads of the e2e run (0 = one per core, max 32)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end measurement (kernel experiments only)")
     ap.add_argument("--prepare-reference", action="store_true",
                     help="internal (child of --impl reference): write part 0 in the reference's format + the read sample, exit")
     ap.add_argument("--replicate", action="store_true",
@@ -693,7 +694,9 @@ def main():
 
     # ---------------- e2e: host buffers through the batch API (H2D + kernels + D2H) -----------
     e2e = None
-    if not sharded:
+    if args.no_e2e:
+        host_reads = host_offs = None
+    elif not sharded:
         host_reads = flat.cpu().numpy()
         host_offs = offs.cpu().numpy().astype(np.uint64)
         del d_top
@@ -743,7 +746,7 @@ def main():
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
     parity = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and not args.no_e2e:
         try:
             base = export_reference_db(args, db, wins, 0)
             sample = args.cpu_sample or int(min(nq, max(200_000, 100_000 * threads) * per_read_scale))

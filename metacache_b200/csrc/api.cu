@@ -747,7 +747,7 @@ extern "C" mcb200_workspace* mcb200_workspace_create (mcb200_db* db, uint32_t ma
     ok(ws->codes.ensure(padded / 16 + 64)); ok(ws->amb.ensure(padded / 32 + 64));
     ok(ws->seq_nwin.ensure(max_seqs + 1)); ok(ws->seq_win_off.ensure(max_seqs + 2));
     ok(ws->qry_win_off.ensure(max_queries + 1));
-    ok(ws->heavy_list.ensure(3 * uint64_t(max_queries))); ok(ws->heavy_count.ensure(6));
+    ok(ws->heavy_list.ensure(4 * uint64_t(max_queries))); ok(ws->heavy_count.ensure(8));
     ok(ws->counters.ensure(64 * 8)); ok(ws->scratch_cursor.ensure(1)); ok(ws->error.ensure(1));
     if (e == cudaSuccess) e = cudaMemset(ws->codes.p, 0, ws->codes.n * 4);
     if (e == cudaSuccess) e = cudaMemset(ws->amb.p, 0xFF, ws->amb.n * 4);
@@ -953,7 +953,7 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
     { int rc = ensure_default_scratch(ws); if (rc) return rc; }
     QueryArgs a = make_args(ws, part, d_top);
     if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
-    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 32, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
     if (ws->profiling && !ws->ev) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
     const bool prof = ws->profiling && ws->ev && ws->ev->q.size() >= (size_t(part) + 1) * 3;
@@ -1071,7 +1071,7 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
     QueryArgs a = make_args(ws, part, d_top);
     ws->q = saved_q; ws->sk = saved_sk;
     a.feats = d_feats; a.qry_win_off = d_qry_win_off;
-    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 32, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
     if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; }
     const bool prof = ws->profiling && ws->ev;
@@ -1167,7 +1167,7 @@ extern "C" int mcb200_shard_reduce_device (mcb200_workspace* ws, uint32_t part, 
     ws->q = saved_q;
     a.feats = nullptr; a.qry_win_off = nullptr; a.tax_of_tgt = nullptr; a.n_tax = 0;
     a.lists = ws->lists.p;
-    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 24, st));
+    CU(cudaMemsetAsync(ws->heavy_count.p, 0, 32, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
     launch_query_lists(a, ws->warp_cap, ws->db->sm_count, st);
     const Part& p = ws->db->parts[part];

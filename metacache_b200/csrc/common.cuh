@@ -123,6 +123,22 @@ __device__ __forceinline__ uint32_t table_find (const TableView& t, uint32_t key
     }
 }
 
+// The same search when the home sector (bucket b) has been loaded ahead of time (software pipelining in
+// the fused kernel: the load is issued while the previous read is still being reduced).
+__device__ __forceinline__ uint32_t table_find_from (const TableView& t, uint32_t key, uint64_t b, Slot s0, Slot s1,
+                                                     uint64_t& data, uint32_t& sectors_read) {
+    ++sectors_read;
+    for (;;) {
+        if (s0.meta != 0 && s0.key == key) { data = s0.data; return s0.meta & kSizeMask; }
+        if (s0.meta == 0) return 0;
+        if (s1.meta != 0 && s1.key == key) { data = s1.data; return s1.meta & kSizeMask; }
+        if (s1.meta == 0) return 0;
+        if (++b == t.nbuckets) b = 0;
+        load_bucket(t.buckets + b, s0, s1);
+        ++sectors_read;
+    }
+}
+
 // ---- warp helpers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id () { return threadIdx.x & 31u; }
 

@@ -109,8 +109,8 @@ struct QueryArgs {
     uint64_t*       allhits;      // null if not wanted
     const uint64_t* allhits_off;  // [nq+1] for this part
     // heavy-query machinery
-    uint32_t*       heavy_list;   // [3][nq_cap] overflow queues: warp kernel pass -> pass / CTA tier -> CTA tier
-    uint32_t*       heavy_count;  // [3][2]: [0] = appended, [1] = consumed (work queues)
+    uint32_t*       heavy_list;   // [4][nq_cap] overflow queues: warp kernel pass -> pass -> sorting pass / CTA tier -> CTA tier
+    uint32_t*       heavy_count;  // [4][2]: [0] = appended, [1] = consumed (work queues)
     uint64_t*       scratch;      // global scratch for huge queries (entries of 8 B + 4 B)
     uint64_t        scratch_entries;
     unsigned long long* scratch_cursor;

@@ -204,6 +204,7 @@ __device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint
 // then the CTA kernel.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kMaxLookupW = 8;
+constexpr int      kDefaultPrefetch = 1;      // see query_fast_kernel: kPf
 constexpr uint32_t kMaxProbe   = 48;
 
 // Key type of the aggregation table: the table's own 32-bit packed location when the part is
@@ -299,7 +300,9 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
 // larger table).  Reads this pass cannot settle go to out_queue.
 // kLists: the read's locations come as one run per owner shard (a.lists, feature-space sharding,
 // kernels_shard.cu) instead of from the local table; everything after the aggregation is the same.
-template <class K, bool kLists>
+// kPf: software pipelining of the next read (table mode): 0 none, 1 header + first features in registers and
+// the home sectors prefetched into L2, 2 the home sectors loaded into registers as well (more registers)
+template <class K, bool kLists, int kPf = 0>
 __global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
@@ -338,22 +341,46 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     const uint32_t n_in = (in_queue >= 0) ? a.heavy_count[2 * in_queue] : a.nq;
     uint32_t* out_list = a.heavy_list + size_t(out_queue) * a.nq_cap;
     uint32_t* out_count = a.heavy_count + 2 * out_queue;
+    // Software pipeline over the reads of a warp (table mode): the header of the NEXT read is loaded when the
+    // current one starts, its first 32 features after the aggregation, the home table sector of each of them
+    // before the top-k rounds - so that the four dependent global-memory round trips a read starts with overlap
+    // the previous read's shared-memory work instead of idling the warp.
+    bool pf = false;                                  // the pf_* registers hold this iteration's read
+    uint32_t pf_w0 = 0, pf_w1 = 0, pf_W = 0, pf_f = kNoFeature;
+    Slot pf_s0{}, pf_s1{};
     for (uint32_t qi = blockIdx.x * kQWarps + warp; qi < n_in; qi += nwarps) {
     const uint32_t q = in_list ? in_list[qi] : qi;
     uint32_t nslots = 0;
     const uint32_t* fbase = nullptr;
+    uint32_t W;
     if (!kLists) {
-        const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
+        const uint32_t w0 = pf ? pf_w0 : __ldg(a.qry_win_off + q), w1 = pf ? pf_w1 : __ldg(a.qry_win_off + q + 1);
         nslots = (w1 - w0) * a.s;
         fbase = a.feats + uint64_t(w0) * a.s;
+        W = pf ? pf_W : __ldg(a.max_win + q);
+    } else W = __ldg(a.max_win + q);
+    const bool pf_now = pf;
+    const uint32_t f_now = pf_f;
+    const Slot s0_now = pf_s0, s1_now = pf_s1;
+    // header of the next read
+    const bool has_next = !kLists && kPf > 0 && (qi + nwarps < n_in);
+    uint32_t nq_ = 0, nw0 = 0, nw1 = 0, nW = 0;
+    if (has_next) {
+        nq_ = in_list ? in_list[qi + nwarps] : qi + nwarps;
+        nw0 = __ldg(a.qry_win_off + nq_); nw1 = __ldg(a.qry_win_off + nq_ + 1); nW = __ldg(a.max_win + nq_);
     }
-    const uint32_t W = __ldg(a.max_win + q);
+    pf = false;
     mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
     uint32_t sectors = 0, nfeat = 0, H = 0, D = 0, list_lines = 0;
 
-    if (W > kMaxLookupW) {            // long reads: the CTA kernel sorts
+    if (W > kMaxLookupW) {            // long reads: the sorting pass / the CTA kernel
         if (lane == 0) out_list[atomicAdd(out_count, 1u)] = q;
         warp_stats(a, false, 0, 0, 0);
+        if (has_next) { pf = true; pf_w0 = nw0; pf_w1 = nw1; pf_W = nW; pf_f = kNoFeature; pf_s0 = Slot{}; pf_s1 = Slot{}; 
+                        // features and sectors of the next read are fetched without overlap this once
+                        const uint32_t nn = (nw1 - nw0) * a.s;
+                        pf_f = (lane < nn) ? __ldg(a.feats + uint64_t(nw0) * a.s + lane) : kNoFeature;
+                        if (kPf == 2 && pf_f != kNoFeature) load_bucket(a.table.buckets + bucket_of(pf_f, a.table.nbuckets), pf_s0, pf_s1); }
         continue;
     }
 
@@ -402,9 +429,14 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     }
     for (uint32_t c = 0; c < nslots && ok; c += 32) {
         const uint32_t idx = c + lane;
-        const uint32_t f = (idx < nslots) ? __ldg(fbase + idx) : kNoFeature;
+        const bool pre = pf_now && c == 0;                       // this chunk was fetched ahead
+        const uint32_t f = pre ? f_now : ((idx < nslots) ? __ldg(fbase + idx) : kNoFeature);
         uint32_t size = 0; uint64_t data = 0;
-        if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
+        if (f != kNoFeature) {
+            size = (kPf == 2 && pre) ? table_find_from(a.table, f, bucket_of(f, a.table.nbuckets), s0_now, s1_now, data, sectors)
+                                     : table_find(a.table, f, data, sectors);
+            ++nfeat;
+        }
         if (size > icap) list_lines += (size * uint32_t(sizeof(K)) + 63u) / 64u;
         const uint32_t incl = warp_incl_scan(size);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
@@ -480,13 +512,17 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
         __syncwarp();
     }
 
+    // first 32 features of the next read (its header has arrived by now)
+    uint32_t nf = kNoFeature;
+    if (has_next) { const uint32_t nn = (nw1 - nw0) * a.s; if (lane < nn) nf = __ldg(a.feats + uint64_t(nw0) * a.s + lane); }
+
+    uint32_t c1 = 0, c2 = 0, f1 = 0, f2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
     if (ok && H != 0) {
         // ---- hits of the window ranges ending at the (one or two) windows of every table entry;
         //      lane-local best and best of another target; order: (hits desc, location asc) ----
         // `far` = distance from the end window of a range to its first occupied window: the candidate's
         // window range is [end - far, end] (what the reference's scan keeps in `fst`), found with the
         // same lookups as the sums
-        uint32_t c1 = 0, c2 = 0, f1 = 0, f2 = 0; K k1 = AK::kEmpty, k2 = AK::kEmpty;
         for (uint32_t j = lane; j < D; j += 32) {
             const uint32_t slot = list[j];
             const K kb = hkeys[slot];
@@ -515,6 +551,17 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
             } else if (AK::tgt(k, wb) != AK::tgt(k1, wb) && (c > c2 || (c == c2 && k < k2))) { c2 = c; k2 = k; f2 = f; }
         }
         __syncwarp();
+    }
+    // home sectors of the next read's features: in flight during the top-k rounds and the table clean-up
+    if (has_next) {
+        pf = true; pf_w0 = nw0; pf_w1 = nw1; pf_W = nW; pf_f = nf;
+        if (nf != kNoFeature) {
+            const Bucket* hb = a.table.buckets + bucket_of(nf, a.table.nbuckets);
+            if (kPf == 2) load_bucket(hb, pf_s0, pf_s1);
+            else asm volatile("prefetch.global.L2 [%0];" :: "l"(hb));
+        }
+    }
+    if (ok && H != 0) {
         // ---- top-k distinct targets ----------------------------------------------
         uint32_t c = 0, last = 0xFFFFFFFFu;
         for (; c < a.maxc; ++c) {
@@ -570,9 +617,13 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     }
 }
 
+// in_queue < 0: all reads of the batch (grid covers them); else the reads of that overflow queue, walked
+// with a grid stride (third pass of the top-hits path: reads whose window range is too long for the
+// neighbour lookups of query_fast_kernel are reduced over their SORTED distinct locations here).
+// Reads whose distinct locations do not fit the table go to out_queue.
 template <bool kTax>
 __global__ void __launch_bounds__(kQWarps * 32)
-query_warp_kernel (QueryArgs a, uint32_t T)
+query_warp_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -585,10 +636,13 @@ query_warp_kernel (QueryArgs a, uint32_t T)
     uint32_t* misc  = pcnt + T;                   // [0] distinct counter, [1..] chosen targets
     const uint32_t mask = T - 1, dmax = T / 2;
 
-    const uint32_t q = blockIdx.x * kQWarps + warp;
+    const uint32_t* in_list = (in_queue >= 0) ? a.heavy_list + size_t(in_queue) * a.nq_cap : nullptr;
+    const uint32_t n_in = (in_queue >= 0) ? a.heavy_count[2 * in_queue] : a.nq;
+    for (uint32_t qi = blockIdx.x * kQWarps + warp; qi < n_in; qi += gridDim.x * kQWarps) {
+    const uint32_t q = in_list ? in_list[qi] : qi;
     uint32_t sectors = 0, nfeat = 0, H = 0;
     bool fused = false;
-    if (q < a.nq) {
+    {
         const uint32_t w0 = __ldg(a.qry_win_off + q), w1 = __ldg(a.qry_win_off + q + 1);
         const uint32_t nslots = (w1 - w0) * a.s;
         const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
@@ -636,7 +690,7 @@ query_warp_kernel (QueryArgs a, uint32_t T)
         __syncwarp();
         const uint32_t D = misc[0];
         if (overflow || D > dmax) {
-            if (lane == 0) a.heavy_list[atomicAdd(a.heavy_count, 1u)] = q;
+            if (lane == 0) a.heavy_list[size_t(out_queue) * a.nq_cap + atomicAdd(a.heavy_count + 2 * out_queue, 1u)] = q;
         } else if (D == 0) {
             fused = true;
             if (lane == 0) write_empty(top, 0, a.maxc);
@@ -777,6 +831,8 @@ query_warp_kernel (QueryArgs a, uint32_t T)
         }
     }
     warp_stats(a, fused, H, nfeat, sectors);
+    __syncwarp();
+    }
 }
 
 static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count, cudaStream_t st, bool lists)
@@ -787,6 +843,8 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
         cudaFuncSetAttribute(query_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -797,11 +855,14 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
         // pass 0: every read, small per-warp tables, full occupancy; pass 1: the reads that overflowed them
         // (queue 0), 1024-slot tables, 1-2 CTAs per SM; what is left (queue 1) goes to the CTA kernel
         static const int cap = [] { const char* e = getenv("MCB200_QUERY_CTAS"); return e ? atoi(e) : 0; }();
+        static const int pfmode = [] { const char* e = getenv("MCB200_PREFETCH"); return e ? atoi(e) : kDefaultPrefetch; }();
         for (int pass = 0; pass < 2; ++pass) {
             const uint32_t Tp = pass == 0 ? T : std::max<uint32_t>(T, kSecondPassSlots);
             const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
             int per_sm = 0;
-            if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false>, kQWarps * 32, smem);
+            if (a.table.win_bits && pfmode == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 2>, kQWarps * 32, smem);
+            else if (a.table.win_bits && pfmode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 1>, kQWarps * 32, smem);
+            else if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false>, kQWarps * 32, smem);
             else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t, false>, kQWarps * 32, smem);
             if (per_sm < 1) per_sm = 1;
             if (pass == 0 && cap >= 1 && cap < per_sm) per_sm = cap;
@@ -814,14 +875,26 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
                 if (a.table.win_bits) query_fast_kernel<uint32_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
                 else                  query_fast_kernel<uint64_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             }
-            else if (a.table.win_bits) query_fast_kernel<uint32_t, false><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            else if (a.table.win_bits) {
+                if (pfmode == 2)      query_fast_kernel<uint32_t, false, 2><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+                else if (pfmode == 1) query_fast_kernel<uint32_t, false, 1><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+                else                  query_fast_kernel<uint32_t, false, 0><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
+            }
             else                       query_fast_kernel<uint64_t, false><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             if (pass == 1) count_launch();
         }
+        if (!lists) {
+            // pass 2: what is left in queue 1 (window ranges longer than kMaxLookupW, or > 512 distinct window
+            // pairs): sort of the distinct locations in a 1024-slot table per warp, one CTA per SM; the rest
+            // (queue 2) goes to the CTA kernel
+            const size_t smem = warp_smem_bytes(kSecondPassSlots) * kQWarps;
+            query_warp_kernel<false><<<unsigned(sm_count), kQWarps * 32, smem, st>>>(a, kSecondPassSlots, 1, 2u);
+            count_launch();
+        }
     } else {
         const size_t smem = warp_smem_bytes(T) * kQWarps;
-        if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T);
-        else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, T);
+        if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T, -1, 0u);
+        else              query_warp_kernel<false><<<grid, kQWarps * 32, smem, st>>>(a, T, -1, 0u);
     }
     count_launch();
 }
@@ -1090,7 +1163,8 @@ static void launch_query_heavy_impl (const QueryArgs& a, int sm_count, cudaStrea
         cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     }
     // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
-    const uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
+    // (sharded lists: fused passes only, queue 1; top hits: fused passes + sorting pass, queue 2)
+    const uint32_t in_queue = lists ? 1u : ((!a.tax_of_tgt && !a.allhits) ? 2u : 0u);
     const size_t small = size_t(kHeavySmallEntries) * 12;
     if (lists) {
         query_heavy_kernel<kHeavySmall, true><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);

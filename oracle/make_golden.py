@@ -227,10 +227,39 @@ def main():
         shutil.copy(os.path.join(tmp, f), os.path.join(C1, f))
     for f in ("single.fa", "pairs.fa", "pair.1.fa", "pair.2.fa", "classified.expected"):
         shutil.copy(os.path.join(tmp, "data", f), os.path.join(C1, f))
+    # what the UNMODIFIED CPU reference built from these sources prints for its own test (test/run_tests:140-168).
+    # Upstream's classified.expected predates two formatting changes of printing.cpp (15-digit fractional
+    # abundances, an extra "--" column in the "unclassified" abundance row: 20 of 36 009 lines), so the drop-in
+    # CLI test compares with this capture exactly and with the upstream file everywhere else.
+    write_cli_capture(mc, tmp)
     shutil.rmtree(tmp)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
 
+CLI_COMMON = ("-no-query-params -mapped-only -precision -ground-truth -tophits -allhits -hits-per-ref "
+              "-abundances -abundance-per species -threads 8")
+
+
+def write_cli_capture(mc, tmp):
+    """oracle/_ref/c1/cli_cpu_reference.out: stdout of the CPU reference `metacache query` for the three
+    FASTA inputs of the reference's own test, run in `tmp` (which holds data/ and the bacteria1 database)"""
+    q = (f"data/single.fa {CLI_COMMON}\ndata/pairs.fa -pairseq {CLI_COMMON}\n"
+         f"data/pair.1.fa data/pair.2.fa -pairfiles {CLI_COMMON}\n")
+    out = subprocess.run([mc, "query", "bacteria1"], input=q, capture_output=True, text=True, cwd=tmp, check=True).stdout
+    with open(os.path.join(C1, "cli_cpu_reference.out"), "w") as f:
+        f.write(out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cli-capture":
+        # only the capture, into an existing oracle/_ref/c1 (needs the reference's test data unpacked)
+        import tarfile
+        t = tempfile.mkdtemp()
+        tarfile.open(os.path.join(REF, "test", "data.tar.gz")).extractall(t)
+        for f in ("bacteria1.meta", "bacteria1.cache0"):
+            shutil.copy(os.path.join(C1, f), os.path.join(t, f))
+        write_cli_capture(refio.METACACHE, t)
+        shutil.rmtree(t)
+    else:
+        main()

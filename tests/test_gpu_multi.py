@@ -141,11 +141,15 @@ def _target_worker(rank, world, port, out_dir):
         nwin = int(cap.item())
         ws = _lib.check_ptr(L.mcb200_workspace_create(db._h, per, dr.n_seqs, dr.n_bases + 64, MAXC, 0))
         sq = ShardedQuery(db, ws, per, nwin, g1.s, MAXC, dev, stream)
-        for _ in range(2):                                      # twice: buffers are reused across steps
-            top = sq.step(dr.q, Sketching(g1.k, g1.s, g1.w, g1.stride), dr.max_win)
-        stream.synchronize()
-        rc = L.mcb200_workspace_check(ws)
-        assert rc == 0, rc
+        for attempt in range(6):                                # re-issued while a scratch pool had to grow (the
+            top = sq.step(dr.q, Sketching(g1.k, g1.s, g1.w, g1.stride), dr.max_win)    # 19 kbp tandem-repeat read)
+            stream.synchronize()
+            rc = L.mcb200_workspace_check(ws)
+            assert rc in (0, _lib.EAGAIN), rc
+            again = torch.tensor([int(rc != 0)], dtype=torch.int64, device=dev)
+            dist.all_reduce(again, op=dist.ReduceOp.MAX)        # every rank takes the same decision
+            if attempt > 0 and not int(again.item()):           # at least twice: buffers are reused across steps
+                break
         out = top.cpu().numpy().view(np.uint32)
     got = [[tuple(int(x) for x in c) for c in row if c[1] > 0] for row in out]
     torch.save(got, os.path.join(out_dir, f"t{rank}.pt"))
