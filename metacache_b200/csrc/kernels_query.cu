@@ -203,8 +203,14 @@ __device__ __forceinline__ void warp_stats (const QueryArgs& a, bool fused, uint
 // settle (table too full, W too large) move to the next queue: a second pass with larger tables,
 // then the CTA kernel.
 // ---------------------------------------------------------------------------
-constexpr uint32_t kMaxLookupW = 8;
-constexpr int      kDefaultPrefetch = 1;      // see query_fast_kernel: kPf
+// Window ranges up to this many windows are summed with neighbour lookups in the aggregation table
+// (ceil((W-1)/2) lookups per distinct window pair); longer ones (reads beyond ~2.5 kbp) go to the CTA kernel.
+// (Sorting the distinct locations per WARP for them - query_warp_kernel as a third pass - was measured and
+// lost: 8 warps per SM at 1024-slot tables; C3 110 ms vs 85 ms.)
+constexpr uint32_t kMaxLookupW = 24;
+// Software pipelining of the next read was measured on C2 and lost to the occupancy it costs (kernel 15.05 ms
+// without, 23.4 ms with L2 prefetches at 48 registers, 16.4 ms with the sectors in registers at 60): off.
+constexpr int      kDefaultPrefetch = 0;
 constexpr uint32_t kMaxProbe   = 48;
 
 // Key type of the aggregation table: the table's own 32-bit packed location when the part is
@@ -373,7 +379,9 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
     uint32_t sectors = 0, nfeat = 0, H = 0, D = 0, list_lines = 0;
 
-    if (W > kMaxLookupW) {            // long reads: the sorting pass / the CTA kernel
+    // long window ranges: the CTA kernel; reads with more than four windows' worth of features would overflow
+    // the small tables of the first pass anyway: straight to the second pass
+    if (W > kMaxLookupW || (in_queue < 0 && T < kSecondPassSlots && nslots > 64)) {
         if (lane == 0) out_list[atomicAdd(out_count, 1u)] = q;
         warp_stats(a, false, 0, 0, 0);
         if (has_next) { pf = true; pf_w0 = nw0; pf_w1 = nw1; pf_W = nW; pf_f = kNoFeature; pf_s0 = Slot{}; pf_s1 = Slot{}; 
@@ -544,7 +552,7 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
             const bool odd = (n1 != 0) && (n0 == 0 || h1 > h0);
             const uint32_t c = odd ? h1 : h0, f = odd ? far1 : far0;
             const K k = K((kb << 1) | K(odd));
-            hits[j] = (c << 4) | (f << 1) | uint32_t(odd);
+            hits[j] = (c << 6) | (f << 1) | uint32_t(odd);
             if (c > c1 || (c == c1 && k < k1)) {
                 if (c1 != 0 && AK::tgt(k1, wb) != AK::tgt(k, wb)) { c2 = c1; k2 = k1; f2 = f1; }
                 c1 = c; k1 = k; f1 = f;
@@ -577,8 +585,8 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
                     const uint32_t tgt = AK::tgt(k, wb);
                     bool taken = false;
                     for (uint32_t i = 0; i < c; ++i) taken |= (chosen[i] == tgt);
-                    const uint32_t cj = e >> 4;
-                    if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; best_f = (e >> 1) & 7u; }
+                    const uint32_t cj = e >> 6;
+                    if (!taken && (cj > best_c || (cj == best_c && k < best_k))) { best_c = cj; best_k = k; best_f = (e >> 1) & 31u; }
                 }
             }
             const uint32_t wmax = __reduce_max_sync(kFull, best_c);
@@ -883,14 +891,6 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
             else                       query_fast_kernel<uint64_t, false><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             if (pass == 1) count_launch();
         }
-        if (!lists) {
-            // pass 2: what is left in queue 1 (window ranges longer than kMaxLookupW, or > 512 distinct window
-            // pairs): sort of the distinct locations in a 1024-slot table per warp, one CTA per SM; the rest
-            // (queue 2) goes to the CTA kernel
-            const size_t smem = warp_smem_bytes(kSecondPassSlots) * kQWarps;
-            query_warp_kernel<false><<<unsigned(sm_count), kQWarps * 32, smem, st>>>(a, kSecondPassSlots, 1, 2u);
-            count_launch();
-        }
     } else {
         const size_t smem = warp_smem_bytes(T) * kQWarps;
         if (a.tax_of_tgt) query_warp_kernel<true><<<grid, kQWarps * 32, smem, st>>>(a, T, -1, 0u);
@@ -1163,8 +1163,7 @@ static void launch_query_heavy_impl (const QueryArgs& a, int sm_count, cudaStrea
         cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     }
     // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
-    // (sharded lists: fused passes only, queue 1; top hits: fused passes + sorting pass, queue 2)
-    const uint32_t in_queue = lists ? 1u : ((!a.tax_of_tgt && !a.allhits) ? 2u : 0u);
+    const uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
     const size_t small = size_t(kHeavySmallEntries) * 12;
     if (lists) {
         query_heavy_kernel<kHeavySmall, true><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);

@@ -10,13 +10,20 @@
  * members exist and throw: building databases is out of scope of this library
  * (it consumes `.cache` files written by the reference's `metacache build`).
  *
+ * Two modes.  Standalone (examples and tests of this repository): the header brings
+ * layout-identical PODs of its own.  In the reference tree (MCB200_IN_REFERENCE_TREE,
+ * defined by the two forwarding headers of host/dropin/ that replace src/gpu_hashmap.cuh
+ * and src/query_batch.cuh): it uses the reference's own types, and the reference's host
+ * program compiles unchanged with -DGPU_MODE (oracle/Makefile: _ref/metacache_mcb200;
+ * tests/test_gpu_dropin.py runs the reference's own CLI test through it).
+ *
  * Differences a maintainer has to know:
  *   - `location` is read/written as the same 8 bytes {u32 win, u32 tgt}.
  *   - `match_candidate::tax` is filled on the host from `target_lineages`
  *     handed to copy_target_lineages_to_gpus (index = rank, as in the reference).
  *   - errors are C++ exceptions (std::runtime_error) instead of CUERR/exit(1).
- *   - one store lives on ONE device (one process per GPU); multi-GPU runs shard
- *     parts over processes and merge candidates (mcb200_merge_candidates_device).
+ *   - a multi-part store takes one GPU per part when the box has them
+ *     (mcb200_db_open_multi, one process); MCB200_DEVICES / MCB200_DEVICE override.
  ******************************************************************************/
 #ifndef MCB200_SHIM_HPP
 #define MCB200_SHIM_HPP
