@@ -1149,6 +1149,182 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
     }
 }
 
+// ---------------------------------------------------------------------------
+// long reads (top hits, rank sequence): one CTA per read that aggregates DISTINCT locations in a
+// shared-memory hash table - the per-warp algorithm of query_warp_kernel at CTA scale - instead of sorting
+// the raw location list: a 5 kbp read returns ~5 000 locations but ~1 300 distinct ones, and the table is
+// probed once, not twice.  Reads with more than kCtaDistinct distinct locations go on to the sorting tiers.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kCtaHashSlots = 8192, kCtaDistinct = 4096;
+constexpr int      kCtaHashThreads = 1024;
+constexpr size_t   kCtaHashSmem = size_t(kCtaHashSlots) * 12 + size_t(kCtaDistinct) * 12;
+
+__global__ void __launch_bounds__(kCtaHashThreads)
+query_cta_hash_kernel (QueryArgs a, uint32_t in_queue, uint32_t out_queue)
+{
+    constexpr int NT = kCtaHashThreads;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* hkeys = reinterpret_cast<uint64_t*>(smem_raw);                   // [kCtaHashSlots]
+    uint64_t* skeys = hkeys + kCtaHashSlots;                                   // [kCtaDistinct] sorted distinct locations
+    uint32_t* hcnt  = reinterpret_cast<uint32_t*>(skeys + kCtaDistinct);       // [kCtaHashSlots] counts, later hits(j)
+    uint32_t* spre  = hcnt + kCtaHashSlots;                                    // [kCtaDistinct] inclusive prefix of the counts
+    __shared__ uint32_t s_base[NT + 1];
+    __shared__ uint64_t s_data[NT];
+    __shared__ uint32_t s_warp[NT / 32];
+    __shared__ uint32_t s_chosen[kMaxCand];
+    __shared__ uint32_t s_red_c[NT / 32], s_red_j[NT / 32];
+    __shared__ uint32_t s_q, s_bc, s_D, s_n, s_fail;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    constexpr uint32_t mask = kCtaHashSlots - 1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t* list = a.heavy_list + size_t(in_queue) * a.nq_cap;
+            uint32_t* count = a.heavy_count + 2 * in_queue;
+            const uint32_t i = atomicAdd(count + 1, 1u);
+            s_q = (i < *reinterpret_cast<volatile uint32_t*>(count)) ? list[i] : 0xFFFFFFFFu;
+            s_D = 0; s_n = 0; s_fail = 0;
+        }
+        for (uint32_t i = tid; i < kCtaHashSlots; i += NT) { hkeys[i] = kEmptyKey; hcnt[i] = 0; }
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q == 0xFFFFFFFFu) break;
+        const uint32_t w0 = a.qry_win_off[q], w1 = a.qry_win_off[q + 1];
+        const uint32_t nslots = (w1 - w0) * a.s;
+        const uint32_t* fbase = a.feats + uint64_t(w0) * a.s;
+        mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
+        const uint32_t W = a.max_win[q];
+        uint32_t sectors = 0, nfeat = 0, H = 0;
+
+        // ---- probe once; every location of the chunk's buckets goes into the table --------------
+        for (uint32_t c = 0; c < nslots; c += NT) {
+            const uint32_t idx = c + tid;
+            const uint32_t f = (idx < nslots) ? fbase[idx] : kNoFeature;
+            uint32_t size = 0; uint64_t data = 0;
+            if (f != kNoFeature) { size = table_find(a.table, f, data, sectors); ++nfeat; }
+            uint32_t total = 0;
+            const uint32_t excl = block_excl_scan<NT>(size, s_warp, total);
+            s_base[tid] = excl;
+            s_data[tid] = data;
+            if (tid == NT - 1) s_base[NT] = total;
+            __syncthreads();
+            H += total;
+            if (!s_fail) {
+                for (uint32_t p = tid; p < total; p += NT) {
+                    uint32_t b = 0;
+                    #pragma unroll
+                    for (uint32_t step = NT / 2; step > 0; step >>= 1)
+                        if (s_base[b + step] <= p) b += step;
+                    const uint32_t sb = s_base[b];
+                    const uint64_t v = bucket_loc(a.table, s_data[b], s_base[b + 1] - sb, p - sb);
+                    uint32_t h = loc_hash(v) & mask;
+                    for (;;) {
+                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(hkeys + h), kEmptyKey, v);
+                        if (old == kEmptyKey) { if (atomicAdd(&s_D, 1u) >= kCtaDistinct) s_fail = 1; atomicAdd(hcnt + h, 1u); break; }
+                        if (old == v) { atomicAdd(hcnt + h, 1u); break; }
+                        h = (h + 1) & mask;
+                        if (*reinterpret_cast<volatile uint32_t*>(&s_fail)) break;        // table filling up: give up
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (s_fail) {                                   // too many distinct locations: the sorting tiers
+            if (tid == 0) a.heavy_list[size_t(out_queue) * a.nq_cap + atomicAdd(a.heavy_count + 2 * out_queue, 1u)] = q;
+            continue;
+        }
+        const uint32_t D = s_D;
+        if (D == 0) { if (tid == 0) write_empty(top, 0, a.maxc); continue; }
+
+        // ---- distinct locations, sorted ------------------------------------------------------------
+        for (uint32_t i = tid; i < kCtaHashSlots; i += NT) {
+            const uint64_t k = hkeys[i];
+            if (k != kEmptyKey) skeys[atomicAdd(&s_n, 1u)] = k;
+        }
+        const uint32_t n = max(pow2_ceil(D), 2u);
+        __syncthreads();
+        for (uint32_t i = D + tid; i < n; i += NT) skeys[i] = kPadKey;
+        __syncthreads();
+        block_bitonic_sort<NT>(skeys, n);
+
+        // ---- multiplicities in sorted order -> inclusive prefix sums (4 consecutive entries per thread) ----
+        {
+            uint32_t cnt4[4], tsum = 0;
+            #pragma unroll
+            for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t j = tid * 4 + i;
+                uint32_t c = 0;
+                if (j < D) {
+                    const uint64_t k = skeys[j];
+                    uint32_t h = loc_hash(k) & mask;
+                    while (hkeys[h] != k) h = (h + 1) & mask;
+                    c = hcnt[h];
+                }
+                cnt4[i] = c; tsum += c;
+            }
+            uint32_t total = 0;
+            uint32_t run = block_excl_scan<NT>(tsum, s_warp, total);
+            #pragma unroll
+            for (uint32_t i = 0; i < 4; ++i) { run += cnt4[i]; if (tid * 4 + i < D) spre[tid * 4 + i] = run; }
+        }
+        __syncthreads();
+        // ---- hits(j): locations of the same target inside the window range ending at j ------------------
+        uint32_t* hitsv = hcnt;                          // the table's counts are no longer needed
+        for (uint32_t j = tid; j < D; j += NT) {
+            uint32_t c = 1;
+            if (W > 0) {
+                const uint32_t f = (W > 1) ? lower_bound_u64(skeys, j, window_floor_key(skeys[j], W)) : j;
+                c = spre[j] - (f ? spre[f - 1] : 0u);
+            }
+            hitsv[j] = c;
+        }
+        __syncthreads();
+        // ---- top-k distinct targets: most hits, smallest (tgt, win) on ties ----------------------------
+        uint32_t c = 0;
+        for (; c < a.maxc; ++c) {
+            uint32_t best_c = 0, best_j = 0xFFFFFFFFu;
+            for (uint32_t j = tid; j < D; j += NT) {
+                const uint32_t tgt = uint32_t(skeys[j] >> 32);
+                bool taken = false;
+                for (uint32_t i = 0; i < c; ++i) taken |= (s_chosen[i] == tgt);
+                const uint32_t cj = hitsv[j];
+                if (!taken && cj > best_c) { best_c = cj; best_j = j; }
+            }
+            const uint32_t wmax = __reduce_max_sync(kFull, best_c);
+            const uint32_t wj = __reduce_min_sync(kFull, best_c == wmax ? best_j : 0xFFFFFFFFu);
+            if (lane == 0) { s_red_c[warp] = wmax; s_red_j[warp] = wj; }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t bc = 0, bj = 0xFFFFFFFFu;
+                for (int i = 0; i < NT / 32; ++i)
+                    if (s_red_c[i] > bc || (s_red_c[i] == bc && s_red_j[i] < bj)) { bc = s_red_c[i]; bj = s_red_j[i]; }
+                s_bc = bc;
+                if (bc > 0) {
+                    const uint64_t ke = skeys[bj];
+                    uint32_t f = bj;
+                    if (W > 1) f = lower_bound_u64(skeys, bj, window_floor_key(ke, W));
+                    top[c] = mcb200_candidate{uint32_t(ke >> 32), bc, uint32_t(skeys[f]), uint32_t(ke)};
+                    s_chosen[c] = uint32_t(ke >> 32);
+                }
+            }
+            __syncthreads();
+            if (s_bc == 0) break;
+        }
+        if (tid == 0) write_empty(top, c, a.maxc);
+        if (a.counters) {
+            const uint32_t sec = __reduce_add_sync(kFull, sectors);
+            const uint32_t nf  = __reduce_add_sync(kFull, nfeat);
+            if (lane == 0) {
+                unsigned long long* cn = a.counters + ((blockIdx.x * (NT / 32) + warp) % kCounterSlots) * 8;
+                atomicAdd(cn + 4, (unsigned long long)nf);
+                atomicAdd(cn + 5, (unsigned long long)sec);
+                if (tid == 0) { atomicAdd(cn + 1, 1ull); atomicAdd(cn + 3, (unsigned long long)H); }
+            }
+        }
+    }
+}
+
 constexpr uint32_t kHeavySmemEntries  = 16384;   // tier 1: 16384 * 12 B = 192 KB, one CTA per SM
 constexpr uint32_t kHeavySmallEntries = 2048;    // tier 0: 24 KB, up to 8 CTAs per SM
 constexpr int      kHeavySmall = 256;            // threads per CTA, tier 0
@@ -1163,8 +1339,17 @@ static void launch_query_heavy_impl (const QueryArgs& a, int sm_count, cudaStrea
         cudaFuncSetAttribute(query_heavy_kernel<kHeavyBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     }
     // the fused kernel ran two passes and left its rest in queue 1; the sorting warp kernel fills queue 0
-    const uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
+    uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
     const size_t small = size_t(kHeavySmallEntries) * 12;
+    if (!lists && !a.tax_of_tgt && !a.allhits) {
+        // top hits from the table: the distinct-location CTA tier first (queue 1 -> 2), then the sorting tiers
+        static std::atomic<uint64_t> attr2{0};
+        if (first_use_on_device(attr2))
+            cudaFuncSetAttribute(query_cta_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCtaHashSmem));
+        query_cta_hash_kernel<<<sm_count, kCtaHashThreads, kCtaHashSmem, st>>>(a, 1u, 2u);
+        count_launch();
+        in_queue = 2u;
+    }
     if (lists) {
         query_heavy_kernel<kHeavySmall, true><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);
         query_heavy_kernel<kHeavyBig, true><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, in_queue + 1, a.nq_cap);
