@@ -243,6 +243,15 @@ template <> struct AggKey<uint64_t> {
 };
 
 constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk staged in shared memory
+constexpr uint32_t kFilterMinLocations = 160;     // lists mode: reads with more locations go through the single-hit filter
+
+template <class K> __device__ __forceinline__ K warp_min_key (K v);
+template <> __device__ __forceinline__ uint32_t warp_min_key<uint32_t> (uint32_t v) { return __reduce_min_sync(kFull, v); }
+template <> __device__ __forceinline__ uint64_t warp_min_key<uint64_t> (uint64_t v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const uint64_t o = __shfl_xor_sync(kFull, v, d); v = o < v ? o : v; }
+    return v;
+}
 constexpr uint32_t kSecondPassSlots = 1024;   // per-warp table of the second pass of the fused kernel
 
 template <class K>
@@ -415,23 +424,88 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
         ssec[lane] = b;
         if (lane == 31) sbase[32] = total;
         __syncwarp();
-        for (uint32_t p0 = 0; p0 < total && ok; p0 += 128) {
-            K v[4];
+        auto load_loc = [&] (uint32_t p) -> K {
+            if (p >= total) return AK::kEmpty;
+            uint32_t o = 0;
             #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t p = p0 + u * 32 + lane;
-                v[u] = AK::kEmpty;
-                if (p < total) {
-                    uint32_t o = 0;
-                    #pragma unroll
-                    for (uint32_t step = 16; step > 0; step >>= 1)
-                        if (sbase[o + step] <= p) o += step;
-                    v[u] = __ldg(static_cast<const K*>(la.src[o].locs) + ssec[o] + (p - sbase[o]));
+            for (uint32_t step = 16; step > 0; step >>= 1)
+                if (sbase[o + step] <= p) o += step;
+            return __ldg(static_cast<const K*>(la.src[o].locs) + ssec[o] + (p - sbase[o]));
+        };
+        // Large databases return mostly UNRELATED single hits (one location of a target that shares a
+        // k-mer by chance): with N database parts merged per feature a 150 bp read brings ~100 related
+        // and ~40 N unrelated locations.  A location whose target occurs once in the read has hits = 1 and
+        // can only be chosen when fewer than maxc targets do better - and then only the smallest such
+        // locations can.  So: pass A marks the targets seen once / more than once in two bitmaps (hash of
+        // the target; a collision only lets a single hit through), pass B aggregates the locations of
+        // targets seen more than once and keeps the two smallest single hits, which are added at the end.
+        // Exact for maxc <= 2; the table then holds the related targets only and stays small.
+        const bool filt = a.maxc <= 2 && total > kFilterMinLocations;
+        if (!filt) {
+            for (uint32_t p0 = 0; p0 < total && ok; p0 += 128) {
+                K v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = load_loc(p0 + u * 32 + lane);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok) ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, v[u] != AK::kEmpty, v[u], D);
+            }
+        } else {
+            // the bitmaps live in hits[] (free until the window sums): 2^fb bits each
+            const uint32_t fb = 31u - __clz((T / 2 + 32) / 2) + 5u;                 // log2(bits per bitmap)
+            uint32_t* seen = hits;
+            uint32_t* dup  = hits + (1u << (fb - 5u));
+            for (uint32_t i = lane; i < (2u << (fb - 5u)); i += 32) hits[i] = 0;
+            __syncwarp();
+            for (uint32_t p0 = 0; p0 < total; p0 += 128) {
+                K v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = load_loc(p0 + u * 32 + lane);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (v[u] != AK::kEmpty) {
+                        const uint32_t h = (AK::tgt(v[u], wb) * 0x9E3779B1u) >> (32u - fb), bit = 1u << (h & 31u);
+                        if (atomicOr(seen + (h >> 5), bit) & bit) atomicOr(dup + (h >> 5), bit);
+                    }
                 }
             }
-            #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (ok) ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, v[u] != AK::kEmpty, v[u], D);
+            __syncwarp();
+            K m1 = AK::kEmpty, m2 = AK::kEmpty;                                      // this lane's two smallest single hits
+            uint32_t staged = 0;
+            for (uint32_t p0 = 0; p0 < total && ok; p0 += 128) {
+                K v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = load_loc(p0 + u * 32 + lane);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    bool keep = false;
+                    if (v[u] != AK::kEmpty) {
+                        const uint32_t h = (AK::tgt(v[u], wb) * 0x9E3779B1u) >> (32u - fb);
+                        keep = (dup[h >> 5] >> (h & 31u)) & 1u;
+                        if (!keep) { if (v[u] < m1) { m2 = m1; m1 = v[u]; } else if (v[u] < m2) m2 = v[u]; }
+                    }
+                    const uint32_t km = __ballot_sync(kFull, keep);
+                    if (keep) stage[staged + __popc(km & ((1u << lane) - 1u))] = v[u];
+                    staged += __popc(km);
+                }
+                if (staged > kStage - 128 || p0 + 128 >= total) {                   // flush the compacted survivors
+                    __syncwarp();
+                    for (uint32_t s0 = 0; s0 < staged && ok; s0 += 32) {
+                        const uint32_t i = s0 + lane;
+                        ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, i < staged, i < staged ? stage[i] : AK::kEmpty, D);
+                    }
+                    staged = 0;
+                    __syncwarp();
+                }
+            }
+            if (ok) {
+                // the two smallest single hits of the read (all single hits have different targets)
+                const K g1 = warp_min_key<K>(m1);
+                if (m1 == g1) m1 = m2;
+                const K g2 = warp_min_key<K>(m1);
+                const K mine = lane == 0 ? g1 : (lane == 1 ? g2 : AK::kEmpty);
+                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, mine != AK::kEmpty, mine, D);
+            }
         }
         __syncwarp();
     }
@@ -1155,14 +1229,13 @@ query_heavy_kernel (QueryArgs a, uint32_t cap_smem, uint32_t tier, uint32_t in_q
 // the raw location list: a 5 kbp read returns ~5 000 locations but ~1 300 distinct ones, and the table is
 // probed once, not twice.  Reads with more than kCtaDistinct distinct locations go on to the sorting tiers.
 // ---------------------------------------------------------------------------
-constexpr uint32_t kCtaHashSlots = 8192, kCtaDistinct = 4096;
-constexpr int      kCtaHashThreads = 1024;
-constexpr size_t   kCtaHashSmem = size_t(kCtaHashSlots) * 12 + size_t(kCtaDistinct) * 12;
-
-__global__ void __launch_bounds__(kCtaHashThreads)
+// Two sizes: 256 threads / 2 048 slots / <= 1 024 distinct locations (36 KB: six CTAs per SM, so the
+// barriers of the block sort overlap across CTAs), then 1 024 threads / 8 192 slots / <= 4 096 distinct.
+template <int NT>
+__global__ void __launch_bounds__(NT)
 query_cta_hash_kernel (QueryArgs a, uint32_t in_queue, uint32_t out_queue)
 {
-    constexpr int NT = kCtaHashThreads;
+    constexpr uint32_t kCtaHashSlots = 8u * NT, kCtaDistinct = 4u * NT;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* hkeys = reinterpret_cast<uint64_t*>(smem_raw);                   // [kCtaHashSlots]
     uint64_t* skeys = hkeys + kCtaHashSlots;                                   // [kCtaDistinct] sorted distinct locations
@@ -1196,6 +1269,10 @@ query_cta_hash_kernel (QueryArgs a, uint32_t in_queue, uint32_t out_queue)
         mcb200_candidate* top = a.top + uint64_t(q) * a.maxc;
         const uint32_t W = a.max_win[q];
         uint32_t sectors = 0, nfeat = 0, H = 0;
+        if (NT < 1024 && nslots > 64u * NT) {           // certainly too many distinct locations for the small size
+            if (tid == 0) a.heavy_list[size_t(out_queue) * a.nq_cap + atomicAdd(a.heavy_count + 2 * out_queue, 1u)] = q;
+            continue;
+        }
 
         // ---- probe once; every location of the chunk's buckets goes into the table --------------
         for (uint32_t c = 0; c < nslots; c += NT) {
@@ -1342,13 +1419,18 @@ static void launch_query_heavy_impl (const QueryArgs& a, int sm_count, cudaStrea
     uint32_t in_queue = (lists || (!a.tax_of_tgt && !a.allhits)) ? 1u : 0u;
     const size_t small = size_t(kHeavySmallEntries) * 12;
     if (!lists && !a.tax_of_tgt && !a.allhits) {
-        // top hits from the table: the distinct-location CTA tier first (queue 1 -> 2), then the sorting tiers
+        // top hits from the table: the distinct-location CTA tiers (queue 1 -> 2 -> 3), then the big sorting tier
         static std::atomic<uint64_t> attr2{0};
-        if (first_use_on_device(attr2))
-            cudaFuncSetAttribute(query_cta_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCtaHashSmem));
-        query_cta_hash_kernel<<<sm_count, kCtaHashThreads, kCtaHashSmem, st>>>(a, 1u, 2u);
-        count_launch();
-        in_queue = 2u;
+        constexpr size_t smem_s = size_t(8 * 256) * 12 + size_t(4 * 256) * 12, smem_l = size_t(8 * 1024) * 12 + size_t(4 * 1024) * 12;
+        if (first_use_on_device(attr2)) {
+            cudaFuncSetAttribute(query_cta_hash_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_s));
+            cudaFuncSetAttribute(query_cta_hash_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_l));
+        }
+        query_cta_hash_kernel<256><<<sm_count * 5, 256, smem_s, st>>>(a, 1u, 2u);
+        query_cta_hash_kernel<1024><<<sm_count, 1024, smem_l, st>>>(a, 2u, 3u);
+        query_heavy_kernel<kHeavyBig, false><<<sm_count, kHeavyBig, smem, st>>>(a, kHeavySmemEntries, 1, 3u, a.nq_cap);
+        count_launch(3);
+        return;
     }
     if (lists) {
         query_heavy_kernel<kHeavySmall, true><<<sm_count * 8, kHeavySmall, small, st>>>(a, kHeavySmallEntries, 0, in_queue, a.nq_cap);

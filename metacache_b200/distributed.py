@@ -266,8 +266,11 @@ class DeviceBackend:
     def reduce(self, slot, pos, runs, max_win, nq, top, mean_locations=0.0):
         """runs: list of (locs tensor, off tensor, n_features, n_locations) per owner"""
         # first-pass table of the fused reduction: large databases return many unrelated single hits
-        # (distinct locations), so size it by the mean list length instead of overflowing to the second pass
+        # (distinct locations); for more than two candidates per read (no filter in the kernel) size it by
+        # the mean list length instead of overflowing to the second pass
         cap = 256 if mean_locations < 160 else (512 if mean_locations < 320 else 1024)
+        if self.k <= 2:
+            cap = 256         # the single-hit filter of the kernel keeps unrelated locations out of the table
         if self._cap.get(slot) != cap:
             _lib.check(self.L.mcb200_workspace_set_warp_capacity(self.ws(slot), cap))
             self._cap[slot] = cap
