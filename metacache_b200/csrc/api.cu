@@ -11,6 +11,16 @@
 #include <string>
 #include <vector>
 
+// NVTX ranges around the host-visible stages (header-only NVTX 3: the calls are no-ops unless a profiler
+// such as Nsight Systems is attached): a submit shows as  mcb200.submit > h2d | sketch | part <p> | merge | d2h
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+    explicit NvtxRange (const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange () { nvtxRangePop(); }
+};
+}
+
 namespace mcb {
 std::atomic<unsigned long long> g_launches{0};
 }
@@ -334,6 +344,23 @@ static int shard_collect (mcb200_db* db, Part& p, const uint32_t* d_keys, const 
     return 0;
 }
 
+// host arrays -> device staging -> insert, all enqueued on the store's stream; the caller decides when
+// the host buffers may be reused (mcb200_db_part_append synchronises, the file loader uses events)
+static int append_host_async (mcb200_db* db, uint32_t part, const uint32_t* keys, const uint8_t* sizes,
+                              const uint64_t* values, uint64_t nkeys, uint64_t nvalues) {
+    CHECK_DB(db, part);
+    Part& p = db->parts[part];
+    if (!p.begun || p.finished) return fail(MCB200_ESTATE, "part %u: append outside begin/finish", part);
+    if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
+        return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
+    if (nkeys == 0) return 0;
+    CU(db->st_keys.ensure(nkeys)); CU(db->st_sizes.ensure(nkeys));
+    CU(cudaMemcpyAsync(db->st_keys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, db->stream));
+    CU(cudaMemcpyAsync(db->st_sizes.p, sizes, nkeys, cudaMemcpyHostToDevice, db->stream));
+    CU(cudaMemcpyAsync(p.values + p.values_loaded, values, nvalues * 8, cudaMemcpyHostToDevice, db->stream));
+    return append_common(db, p, db->st_keys.p, db->st_sizes.p, nkeys, nvalues);
+}
+
 extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32_t* keys,
                                       const uint8_t* sizes, const uint64_t* values,
                                       uint64_t nkeys, uint64_t nvalues) {
@@ -352,14 +379,7 @@ extern "C" int mcb200_db_part_append (mcb200_db* db, uint32_t part, const uint32
         vals.release();
         return rc;
     }
-    if (p.keys_loaded + nkeys > p.nkeys || p.values_loaded + nvalues > p.nvalues)
-        return fail(MCB200_EINVAL, "part %u: more keys/values appended than declared", part);
-    if (nkeys == 0) return 0;
-    CU(db->st_keys.ensure(nkeys)); CU(db->st_sizes.ensure(nkeys));
-    CU(cudaMemcpyAsync(db->st_keys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, db->stream));
-    CU(cudaMemcpyAsync(db->st_sizes.p, sizes, nkeys, cudaMemcpyHostToDevice, db->stream));
-    CU(cudaMemcpyAsync(p.values + p.values_loaded, values, nvalues * 8, cudaMemcpyHostToDevice, db->stream));
-    int rc = append_common(db, p, db->st_keys.p, db->st_sizes.p, nkeys, nvalues);
+    const int rc = append_host_async(db, part, keys, sizes, values, nkeys, nvalues);
     if (rc) return rc;
     CU(cudaStreamSynchronize(db->stream));     // host buffers may be reused by the caller
     return 0;
@@ -537,6 +557,7 @@ extern "C" int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* m
 
 extern "C" int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const char* path,
                                           float max_load_factor) {
+    NvtxRange nvtx_("mcb200.load_cache_file");
     FORWARD_PART(db, part, mcb200_db_load_cache_file(c_, lp_, path, max_load_factor));
     CHECK_DB(db, part);
     FILE* f = fopen(path, "rb");
@@ -546,22 +567,35 @@ extern "C" int mcb200_db_load_cache_file (mcb200_db* db, uint32_t part, const ch
     const uint64_t nkeys = hdr[0], nvalues = hdr[1], batch = hdr[2] ? hdr[2] : (1u << 20);
     int rc = mcb200_db_part_begin(db, part, nkeys, nvalues, max_load_factor);
     if (rc) { fclose(f); return rc; }
-    std::vector<uint32_t> keys; std::vector<uint8_t> sizes; std::vector<uint64_t> vals;
-    for (uint64_t done = 0; done < nkeys; ) {
+    // Two pinned staging sets: the file is read into one while the other one's H2D copies and insert kernel
+    // run (gpu_hashmap.cu:813-912 double-buffers its batches the same way).  The store's stream orders the
+    // device-side staging buffers; an event per set says when its host buffers may be overwritten.
+    struct Stage { PinBuf<uint32_t> keys; PinBuf<uint8_t> sizes; PinBuf<uint64_t> vals; cudaEvent_t done = nullptr; bool busy = false; } st[2];
+    Part& p = db->parts[part];
+    auto cleanup = [&] { for (auto& x : st) { if (x.done) { cudaEventSynchronize(x.done); cudaEventDestroy(x.done); }
+                                              x.keys.release(); x.sizes.release(); x.vals.release(); } fclose(f); };
+    for (auto& x : st) if (cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming) != cudaSuccess) {
+        cleanup(); return fail(MCB200_ECUDA, "loader: event creation failed");
+    }
+    uint64_t i = 0;
+    for (uint64_t done = 0; done < nkeys; ++i) {
+        Stage& x = st[i & 1];
         const uint64_t b = std::min<uint64_t>(batch, nkeys - done);
-        keys.resize(b); sizes.resize(b);
-        if (fread(keys.data(), 4, b, f) != b || fread(sizes.data(), 1, b, f) != b) {
-            fclose(f); return fail(MCB200_EIO, "'%s': truncated batch", path);
-        }
+        if (x.busy && cudaEventSynchronize(x.done) != cudaSuccess) { cleanup(); return fail(MCB200_ECUDA, "loader: %s", cudaGetErrorString(cudaGetLastError())); }
+        if (x.keys.ensure(b) != cudaSuccess || x.sizes.ensure(b) != cudaSuccess) { cleanup(); return fail(MCB200_ENOMEM, "loader: pinned staging"); }
+        if (fread(x.keys.p, 4, b, f) != b || fread(x.sizes.p, 1, b, f) != b) { cleanup(); return fail(MCB200_EIO, "'%s': truncated batch", path); }
         uint64_t nv = 0;
-        for (uint64_t i = 0; i < b; ++i) nv += sizes[i];
-        vals.resize(nv);
-        if (nv && fread(vals.data(), 8, nv, f) != nv) { fclose(f); return fail(MCB200_EIO, "'%s': truncated values", path); }
-        rc = mcb200_db_part_append(db, part, keys.data(), sizes.data(), vals.data(), b, nv);
-        if (rc) { fclose(f); return rc; }
+        for (uint64_t j = 0; j < b; ++j) nv += x.sizes.p[j];
+        if (x.vals.ensure(nv) != cudaSuccess) { cleanup(); return fail(MCB200_ENOMEM, "loader: pinned staging"); }
+        if (nv && fread(x.vals.p, 8, nv, f) != nv) { cleanup(); return fail(MCB200_EIO, "'%s': truncated values", path); }
+        if (p.shard_mode) rc = mcb200_db_part_append(db, part, x.keys.p, x.sizes.p, x.vals.p, b, nv);
+        else              rc = append_host_async(db, part, x.keys.p, x.sizes.p, x.vals.p, b, nv);
+        if (!rc && cudaEventRecord(x.done, db->stream) != cudaSuccess) rc = fail(MCB200_ECUDA, "loader: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc) { cleanup(); return rc; }
+        x.busy = true;
         done += b;
     }
-    fclose(f);
+    cleanup();
     return mcb200_db_part_finish(db, part);
 }
 
@@ -822,6 +856,7 @@ static int sketch_impl (mcb200_workspace* ws, const mcb200_dev_queries* q, const
                     q->n_queries, ws->max_queries, q->n_seqs, ws->max_seqs,
                     (unsigned long long)q->n_bases, (unsigned long long)ws->max_bases);
     if (q->n_seqs < q->n_queries) return fail(MCB200_EINVAL, "every query needs at least one sequence");
+    NvtxRange nvtx_("mcb200.sketch");
     const bool packed = d_codes != nullptr;
     if (packed) {
         if (!d_amb) return fail(MCB200_EINVAL, "packed input needs both the codes and the ambiguity bits");
@@ -950,6 +985,7 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
 
 static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
                        const uint64_t* allhits_off, cudaStream_t st) {
+    NvtxRange nvtx_("mcb200.query_part");
     { int rc = ensure_default_scratch(ws); if (rc) return rc; }
     QueryArgs a = make_args(ws, part, d_top);
     if (allhits_off) { a.allhits = ws->allhits.p; a.allhits_off = allhits_off; }
@@ -972,6 +1008,7 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
 // where every GPU forwards the whole batch to the next one.  The caller makes `st` wait for r->ev_done.
 static int remote_query (mcb200_workspace* ws, uint32_t child, uint32_t local_part, mcb200_candidate* d_dst,
                          cudaStream_t st) {
+    NvtxRange nvtx_("mcb200.query_part.remote_device");
     mcb200_workspace* r = ws->remote[child];
     const int hdev = ws->db->device, rdev = r->db->device;
     const uint32_t nq = ws->q.n_queries, s = ws->sk.s;
@@ -1169,6 +1206,7 @@ extern "C" int mcb200_shard_reduce_device (mcb200_workspace* ws, uint32_t part, 
     a.lists = ws->lists.p;
     CU(cudaMemsetAsync(ws->heavy_count.p, 0, 32, st));
     CU(cudaMemsetAsync(ws->scratch_cursor.p, 0, 8, st));
+    NvtxRange nvtx_("mcb200.shard_reduce");
     launch_query_lists(a, ws->warp_cap, ws->db->sm_count, st);
     const Part& p = ws->db->parts[part];
     if (p.d_tgt_orig) {
@@ -1608,6 +1646,7 @@ extern "C" int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const
     Slot_& s = b->slots[slot];
     if (s.submitted) return fail(MCB200_ESTATE, "slot %u: clear() before adding reads again", slot);
     if (!bases || !offsets || winstride == 0) return fail(MCB200_EINVAL, "bad argument");
+    NvtxRange nvtx_("mcb200.add_reads.pack");
     // the reads are contiguous in `bases` (an empty mate contributes nothing): register them one by
     // one, then pack the whole base range with one call
     int64_t added = 0;
@@ -1638,6 +1677,7 @@ extern "C" int64_t mcb200_batch_add_reads (mcb200_batch* b, uint32_t slot, const
 
 extern "C" int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200_sketching* sk) {
     CHECK_SLOT(b, slot);
+    NvtxRange nvtx_("mcb200.submit");
     Slot_& s = b->slots[slot];
     int rc = validate_sketching(sk);
     if (rc) return rc;
@@ -1678,6 +1718,7 @@ extern "C" int mcb200_batch_submit (mcb200_batch* b, uint32_t slot, const mcb200
 
 extern "C" int mcb200_batch_wait (mcb200_batch* b, uint32_t slot) {
     CHECK_SLOT(b, slot);
+    NvtxRange nvtx_("mcb200.wait");
     Slot_& s = b->slots[slot];
     if (!s.submitted) return fail(MCB200_ESTATE, "slot %u: nothing submitted", slot);
     CU(cudaSetDevice(b->db->device));

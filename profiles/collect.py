@@ -106,7 +106,7 @@ def main(tag):
         if j:
             json.dump(j, open(os.path.join(P, name), "w"), indent=1)
     launches(tag)
-    ncu_text(f"prof_query_{tag}.ncu-rep", f"ncu_query_fast_{tag}", "_ZN3mcb17query_fast_kernelIjEEvNS_9QueryArgsE", 1e6)
+    ncu_text(f"prof_query_{tag}.ncu-rep", f"ncu_query_fast_{tag}", "_ZN3mcb17query_fast_kernelIjLb0ELi0E", 1e6)
     ncu_text(f"prof_sketch_{tag}.ncu-rep", f"ncu_sketch_{tag}", "_ZN3mcb18sketch_fast_kernelE", 2e6)
     for f in ("gather_bench3.log", "exp1.log"):
         if os.path.exists(os.path.join(G, f)):
