@@ -244,7 +244,6 @@ template <> struct AggKey<uint64_t> {
 
 constexpr uint32_t kStage = 256;          // locations of one 32-feature chunk staged in shared memory
 constexpr uint32_t kFilterMinLocations = 160;     // lists mode: reads with more locations go through the single-hit filter
-constexpr uint32_t kTableFilterMinLocations = 16; // table mode (one-chunk reads): likewise
 
 template <class K> __device__ __forceinline__ K warp_min_key (K v);
 template <> __device__ __forceinline__ uint32_t warp_min_key<uint32_t> (uint32_t v) { return __reduce_min_sync(kFull, v); }
@@ -319,7 +318,7 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
 // kPf: software pipelining of the next read (table mode): 0 none, 1 header + first features in registers and
 // the home sectors prefetched into L2, 2 the home sectors loaded into registers as well (more registers)
 template <class K, bool kLists, int kPf = 0>
-__global__ void __launch_bounds__(kQWarps * 32, sizeof(K) == 4 && kPf == 0 ? 6 : 1)
+__global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
     using AK = AggKey<K>;
@@ -565,51 +564,12 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
                 }
             }
             __syncwarp();
-            uint32_t n_agg = total;
-            K g1 = AK::kEmpty, g2 = AK::kEmpty;
-            if (a.maxc <= 2 && nslots <= 32 && total >= kTableFilterMinLocations) {
-                // the single-hit filter (see the lists branch above) on the staged list of a one-chunk read:
-                // unrelated single hits - all a read finds in the parts of a partitioned database it does not
-                // come from - never enter the table, except the two smallest
-                const uint32_t fb = 31u - __clz((T / 2 + 32) / 2) + 5u;
-                uint32_t* seen = hits;
-                uint32_t* dup  = hits + (1u << (fb - 5u));
-                for (uint32_t i = lane; i < (2u << (fb - 5u)); i += 32) hits[i] = 0;
-                __syncwarp();
-                for (uint32_t p = lane; p < total; p += 32) {
-                    const uint32_t h = (AK::tgt(stage[p], wb) * 0x9E3779B1u) >> (32u - fb), bit = 1u << (h & 31u);
-                    if (atomicOr(seen + (h >> 5), bit) & bit) atomicOr(dup + (h >> 5), bit);
-                }
-                __syncwarp();
-                K m1 = AK::kEmpty, m2 = AK::kEmpty;
-                uint32_t kept = 0;
-                for (uint32_t p0 = 0; p0 < total; p0 += 32) {
-                    const uint32_t p = p0 + lane;
-                    bool keep = false;
-                    K v = AK::kEmpty;
-                    if (p < total) {
-                        v = stage[p];
-                        const uint32_t h = (AK::tgt(v, wb) * 0x9E3779B1u) >> (32u - fb);
-                        keep = (dup[h >> 5] >> (h & 31u)) & 1u;
-                        if (!keep) { if (v < m1) { m2 = m1; m1 = v; } else if (v < m2) m2 = v; }
-                    }
-                    const uint32_t km = __ballot_sync(kFull, keep);          // (every lane has read its entry by now)
-                    if (keep) stage[kept + __popc(km & ((1u << lane) - 1u))] = v;
-                    kept += __popc(km);
-                }
-                g1 = warp_min_key<K>(m1);
-                if (m1 == g1) m1 = m2;
-                g2 = warp_min_key<K>(m1);
-                n_agg = kept;
-                __syncwarp();
-            }
-            for (uint32_t p0 = 0; p0 < n_agg && ok; p0 += 32) {
+            // (the single-hit filter of the lists branch was tried here for one-chunk reads - all a read finds in
+            // the parts it does not come from are single hits - and LOST: kernel 16.2 vs 15.05 ms on C2, 15.9 vs
+            // 14.4 ms per part at N=2; two more passes over the staged list cost more than the inserts they save)
+            for (uint32_t p0 = 0; p0 < total && ok; p0 += 32) {
                 const uint32_t p = p0 + lane;
-                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, p < n_agg, p < n_agg ? stage[p] : AK::kEmpty, D);
-            }
-            if (ok && g1 != AK::kEmpty) {
-                const K mine = lane == 0 ? g1 : (lane == 1 ? g2 : AK::kEmpty);
-                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, mine != AK::kEmpty, mine, D);
+                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, p < total, p < total ? stage[p] : AK::kEmpty, D);
             }
         } else {
             __syncwarp();
