@@ -280,7 +280,8 @@ int mcb200_query_device (mcb200_workspace* ws, const mcb200_dev_queries* q,
  * of 32: a call ORs into the word it starts in and stores every further word.
  * Room needed: codes[2 * ((pos + n + 31) / 32 + 1)], amb[(pos + n + 31) / 32 + 1].
  * Before shipping, set the bits of the last amb word beyond the final base.
- * Returns 1 if the AVX2 path ran, 0 for the scalar one, < 0 on error.          */
+ * Returns the SIMD level available to the packer on this host (0 scalar, 1 AVX2,
+ * 2 AVX-512 F+BW; runtime dispatch), < 0 on error.                              */
 int mcb200_pack_bases (const char* bases, uint64_t n, uint64_t pos, uint32_t* codes, uint32_t* amb);
 /* mcb200_sketch_device / mcb200_query_device for reads that are ALREADY packed in
  * device memory (layout above; 16-byte aligned, 64 readable bytes behind the last

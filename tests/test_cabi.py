@@ -43,6 +43,19 @@ def test_fails_loudly_without_a_gpu():
     from metacache_b200.database import Database
     with pytest.raises(_lib.Mcb200Error):
         Database(0, 1)
+    # a store over several devices needs them too; argument errors come first
+    with pytest.raises(_lib.Mcb200Error):
+        Database(devices=[0, 1])
+    assert not L.mcb200_db_open_multi(0, None)
+    assert "n_parts" in L.mcb200_last_error().decode()
+    # null handles are errors, not crashes, on every new entry point
+    assert L.mcb200_db_shard_begin(None, 0, 0, 2, 0) < 0
+    assert L.mcb200_db_shard_finish(None, 0, C.c_float(0), 0, 0) < 0
+    assert L.mcb200_shard_route_device(None, None, None, 0, 16, 2, None, None, None) < 0
+    assert L.mcb200_shard_probe_device(None, 0, None, 0, None, None, None) < 0
+    assert L.mcb200_shard_reduce_device(None, 0, 2, None, None, None, 0, None, None) < 0
+    assert L.mcb200_query_packed_device(None, None, None, None, None, None, None) < 0
+    assert L.mcb200_db_location_bytes(None, 0) == 0 and L.mcb200_db_part_device(None, 0) == -1
 
 
 def test_product_path_never_imports_the_oracle():
