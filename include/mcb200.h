@@ -16,6 +16,8 @@
  *   - locations are u64 = (tgt << 32) | win, i.e. exactly the 8 on-disk bytes
  *     of `database::location{win,tgt}` read as one little-endian u64
  *     (database.hpp:136-166); u64 '<' is location::operator<.
+ *   - caller-owned device buffers of candidates (d_top, d_parts, d_out) must be
+ *     16-byte aligned (one 128-bit store per candidate); cudaMalloc'ed memory is.
  *   - the library owns all pinned-host and device memory it hands out; result
  *     pointers stay valid until the slot is cleared or resubmitted.
  *   - there is NO CPU fallback: without a CUDA device every compute entry

@@ -1071,6 +1071,7 @@ static int join_remotes (mcb200_workspace* ws, cudaStream_t st) {
 extern "C" int mcb200_query_part_device (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_top,
                                          void* stream) {
     if (!ws || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_top) & 15) return fail(MCB200_EINVAL, "candidate buffer must be 16-byte aligned");
     if (!ws->sketched) return fail(MCB200_ESTATE, "mcb200_sketch_device must run first");
     if (!store_part_loaded(ws, part)) return fail(MCB200_ESTATE, "part %u not loaded", part);
     CU(cudaSetDevice(ws->db->device));
@@ -1093,6 +1094,7 @@ extern "C" int mcb200_query_sketches_device (mcb200_workspace* ws, uint32_t part
                                              const uint32_t* d_max_win, uint32_t n_queries,
                                              uint32_t sketchlen, mcb200_candidate* d_top, void* stream) {
     if (!ws || !d_feats || !d_qry_win_off || !d_max_win || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_top) & 15) return fail(MCB200_EINVAL, "candidate buffer must be 16-byte aligned");
     if (sketchlen < 1 || sketchlen > 32) return fail(MCB200_EINVAL, "sketchlen %u unsupported (1..32)", sketchlen);
     if (part >= ws->db->parts.size() || !ws->db->parts[part].finished)
         return fail(MCB200_ESTATE, "part %u not loaded", part);
@@ -1179,6 +1181,7 @@ extern "C" int mcb200_shard_reduce_device (mcb200_workspace* ws, uint32_t part, 
                                            const uint32_t* d_max_win, uint32_t n_queries,
                                            mcb200_candidate* d_top, void* stream) {
     if (!ws || !d_pos || !runs || !d_max_win || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_top) & 15) return fail(MCB200_EINVAL, "candidate buffer must be 16-byte aligned");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(MCB200_EINVAL, "%u shards unsupported (1..%u)", n_shards, kMaxShards);
     if (part >= ws->db->parts.size() || !ws->db->parts[part].finished) return fail(MCB200_ESTATE, "part %u not loaded", part);
     if (n_queries > ws->max_queries) return fail(MCB200_EINVAL, "batch exceeds workspace capacity");
@@ -1250,6 +1253,7 @@ static int query_device_impl (mcb200_workspace* ws, const mcb200_dev_queries* q,
                               const uint32_t* d_amb, const mcb200_sketching* sk, mcb200_candidate* d_top,
                               void* stream) {
     if (!ws || !q || !d_top) return fail(MCB200_EINVAL, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_top) & 15) return fail(MCB200_EINVAL, "candidate buffer must be 16-byte aligned");
     for (uint32_t p = 0; p < store_part_count(ws); ++p)
         if (!store_part_loaded(ws, p)) return fail(MCB200_ESTATE, "database part not loaded");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

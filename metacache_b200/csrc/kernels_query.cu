@@ -57,8 +57,12 @@ __device__ __forceinline__ uint64_t window_floor_key (uint64_t key, uint32_t W) 
     return (key & 0xFFFFFFFF00000000ull) | lo;
 }
 
+// candidate lists are 16-byte aligned (the entry points check it): one 128-bit store per candidate
+__device__ __forceinline__ void store_candidate (mcb200_candidate* p, uint32_t tgt, uint32_t hits, uint32_t beg, uint32_t end) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(tgt, hits, beg, end);
+}
 __device__ __forceinline__ void write_empty (mcb200_candidate* top, uint32_t from, uint32_t maxc) {
-    for (uint32_t c = from; c < maxc; ++c) top[c] = mcb200_candidate{0xFFFFFFFFu, 0u, 0u, 0u};
+    for (uint32_t c = from; c < maxc; ++c) store_candidate(top + c, 0xFFFFFFFFu, 0u, 0u, 0u);
 }
 
 // insert() with taxon merging, sequential (candidate_generation.hpp:172-231);
@@ -675,12 +679,12 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
             if (sizeof(K) == 4) {
                 const uint32_t wk = __reduce_min_sync(kFull, cand ? uint32_t(best_k) : 0xFFFFFFFFu);
                 wt = AK::tgt(K(wk), wb); ww = AK::win(K(wk), wb);
-                if (cand && uint32_t(best_k) == wk) { top[c] = mcb200_candidate{wt, wmax, ww - best_f, ww}; chosen[c] = wt; }
+                if (cand && uint32_t(best_k) == wk) { store_candidate(top + c, wt, wmax, ww - best_f, ww); if (a.maxc > 2) chosen[c] = wt; }
             } else {
                 const uint32_t bt = AK::tgt(best_k, wb), bw = AK::win(best_k, wb);
                 wt = __reduce_min_sync(kFull, cand ? bt : 0xFFFFFFFFu);
                 ww = __reduce_min_sync(kFull, (cand && bt == wt) ? bw : 0xFFFFFFFFu);
-                if (cand && bt == wt && bw == ww) { top[c] = mcb200_candidate{wt, wmax, ww - best_f, ww}; chosen[c] = wt; }
+                if (cand && bt == wt && bw == ww) { store_candidate(top + c, wt, wmax, ww - best_f, ww); if (a.maxc > 2) chosen[c] = wt; }
             }
             last = wt;
             __syncwarp();
