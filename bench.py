@@ -55,6 +55,11 @@ def parse():
     ap.add_argument("--replicate", action="store_true",
                     help="N > 1: every GPU holds the SAME single-part database and queries only its own reads "
                          "(the reference's -replicate mode, SURVEY 8e) instead of the target-sharded database")
+    ap.add_argument("--replicate-merged", action="store_true",
+                    help="N > 1: every GPU holds ALL N parts merged into one table (buckets of a feature concatenated in "
+                         "part order; N x 14 GB fits the 180 GB of a B200 up to N = 8) and queries only its own reads: the "
+                         "N-part database without any exchange.  Not the sharded configuration BASELINE names; reported "
+                         "beside it")
     ap.add_argument("--shard-by", default="target", choices=["feature", "target"],
                     help="N > 1: target = the reference's own partitioning, one part per GPU, every GPU probes every read "
                          "against its part (default: the faster mode on DB-S at every N measured); feature = every GPU owns "
@@ -152,7 +157,7 @@ def build_part(args, part, device):
     return db, bases, wins, info
 
 
-def build_feature_shard(args, rank, world, device):
+def build_feature_shard(args, rank, world, device, all_features=False):
     """Shard `rank` of the feature-sharded database: every rank generates and sketches EVERY part
     (no exchange at load time; ~1 s per part) and keeps the features it owns, with the locations of
     all parts merged per feature.  Returns the bases of part `rank` for the read generator."""
@@ -178,10 +183,13 @@ def build_feature_shard(args, rank, world, device):
             del bases, off
             torch.cuda.empty_cache()
 
-    load_feature_shard(db, rank, world, world * args.targets, feed, TorchComm(), args.load_factor)
+    # all_features: "shard 0 of 1" = every feature, i.e. the whole N-part database merged on this GPU
+    load_feature_shard(db, 0 if all_features else rank, 1 if all_features else world, world * args.targets, feed,
+                       TorchComm(), args.load_factor)
     torch.cuda.synchronize(device)
     info = dict(build_s=round(time.time() - t0, 2), keys=db.key_count(0), locations=db.value_count(0),
-                table_gb=round(db.device_bytes(0) / 1e9, 2), shard="features of all %d parts owned by this rank" % world)
+                table_gb=round(db.device_bytes(0) / 1e9, 2),
+                shard=("all %d parts merged on every GPU" if all_features else "features of all %d parts owned by this rank") % world)
     return db, keep["bases"], keep["wins"], info
 
 
@@ -488,7 +496,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
-    sharded = world > 1 and not args.replicate               # else: independent replicas (or one GPU)
+    sharded = world > 1 and not args.replicate and not args.replicate_merged   # else: independent replicas (or one GPU)
     part = rank if sharded else 0
     threads = os.cpu_count() or 1
 
@@ -499,6 +507,8 @@ def main():
     by_feature = sharded and args.shard_by == "feature"
     if by_feature:
         db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device)
+    elif args.replicate_merged and world > 1:
+        db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device, all_features=True)
     else:
         db, bases, wins, dbinfo = build_part(args, part, device)
     flat, offs = make_reads(args, bases, rank, device)       # uint8 bases back to back + int64 offsets, on the device
@@ -510,6 +520,8 @@ def main():
                  f"{world}-way target-partitioned database ({world * args.targets} targets) sharded by FEATURE over "
                  f"{world} GPUs, features and location lists exchanged over NCCL" if by_feature else
                  f"{world}-way target-partitioned, one part per GPU, every GPU probes every read" if sharded else
+                 f"{world}-way target-partitioned database ({world * args.targets} targets) merged into one table and "
+                 f"replicated on {world} GPUs, every GPU queries its own reads, no exchange" if args.replicate_merged else
                  f"single partition replicated on {world} GPUs, every GPU queries its own reads")
     if args.workload == "C2":
         metric = "reads_per_second_150bp"
@@ -523,7 +535,8 @@ def main():
         read_len = round(n_bases / nq, 1)
     config = {"workload": workload, "reads_per_gpu": nq, "read_len": read_len, "targets_per_part": args.targets,
               "db": dbinfo, "l2": "inputs larger than L2 (reads %.1f GB + table %.1f GB per step)" %
-              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": ("feature-sharded x%d" if by_feature else "db-sharded x%d" if sharded or world == 1 else "replicas x%d") % world}
+              (n_bases / 1e9, dbinfo["table_gb"]), "parallelism": ("feature-sharded x%d" if by_feature else "db-sharded x%d" if sharded or world == 1 else
+                              "merged replicas x%d" if args.replicate_merged else "replicas x%d") % world}
     per_read_scale = READ_LEN * nq / n_bases                 # CPU samples are sized in 150 bp read equivalents
 
     if args.prepare_reference:

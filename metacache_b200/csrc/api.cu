@@ -997,6 +997,16 @@ static int query_part (mcb200_workspace* ws, uint32_t part, mcb200_candidate* d_
     launch_query_warp(a, ws->warp_cap, ws->db->sm_count, st);
     if (prof) CU(cudaEventRecord(ws->ev->q[part * 3 + 1], st));
     launch_query_heavy(a, ws->db->sm_count, st);
+    {   // a merged table numbers targets part-major internally (mcb200_db_shard_finish): back to the ids of the .meta
+        const Part& p = ws->db->parts[part];
+        if (p.d_tgt_orig) {
+            if (allhits_off || ws->db->d_tax)
+                return fail(MCB200_EINVAL, "part %u holds renumbered targets: all-hits output and -lowest above sequence are not available", part);
+            const uint64_t n = uint64_t(ws->q.n_queries) * ws->maxc;
+            translate_targets_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(d_top, n, p.d_tgt_orig, p.n_targets);
+            count_launch();
+        }
+    }
     if (prof) { CU(cudaEventRecord(ws->ev->q[part * 3 + 2], st)); ws->ev->part_done[part] = 1; }
     CU(cudaGetLastError());
     return 0;

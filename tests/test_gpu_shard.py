@@ -146,3 +146,25 @@ def test_routing_agrees_with_the_restated_owner_function():
     assert pos[-1] == (feats != 0xFFFFFFFF).sum()
     L.mcb200_workspace_destroy(ws)
     db.close()
+
+
+def test_all_parts_merged_into_one_table_equal_the_reference_per_part_merge():
+    """"shard 0 of 1": every feature of both parts of golden g2 in ONE table (buckets concatenated in part
+    order, part-major target numbering inside, original ids outside), queried through the ordinary batch API"""
+    from metacache_b200.database import Database, query_reads
+    from metacache_b200.distributed import ThreadComm, load_feature_shard
+    g1, g2 = G1(), G2()
+    db = Database(0, 1)
+
+    def feed(d):
+        for p in g2.parts:
+            d.load_part_arrays(0, *p, batch=30000)
+
+    load_feature_shard(db, 0, 1, len(g1.targets), feed, ThreadComm(ThreadComm.Shared(1), 0))
+    assert db.value_count(0) == sum(len(p[2]) for p in g2.parts)
+    assert db.key_count(0) == len(np.union1d(g2.parts[0][0], g2.parts[1][0]))
+    res = query_reads(db, g1.reads, copy_all_hits=False, batch_queries=500)
+    want = _expected(len(g1.reads))
+    bad = [i for i, (_, top) in enumerate(res) if top != want[i]]
+    assert not bad, (bad[:5], res[bad[0]][1], want[bad[0]])
+    db.close()
