@@ -980,6 +980,8 @@ static QueryArgs make_args (mcb200_workspace* ws, uint32_t part, mcb200_candidat
     a.scratch_cursor = ws->scratch_cursor.p;
     a.counters = ws->profiling ? ws->counters.p : nullptr; a.error = ws->error.p;
     a.lists = nullptr;
+    // a table that merges several parts returns mostly unrelated single hits: stage more, filter them (kernels_query.cu)
+    a.filter_min = p.merged ? 128u : 0u;
     return a;
 }
 

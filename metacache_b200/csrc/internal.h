@@ -117,6 +117,7 @@ struct QueryArgs {
     unsigned long long* counters; // [8] see mcb200_workspace_counters
     int*            error;        // sticky device error flag
     const ListArgs* lists;        // device copy; only read by the *_lists launches
+    uint32_t        filter_min;   // fused kernel, table mode: single-hit filter for reads with at least this many locations (0 = off)
 };
 void launch_query_warp  (const QueryArgs& a, uint32_t cap, int sm_count, cudaStream_t st);
 void launch_query_heavy (const QueryArgs& a, int sm_count, cudaStream_t st);

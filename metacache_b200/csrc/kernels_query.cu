@@ -259,10 +259,10 @@ template <> __device__ __forceinline__ uint64_t warp_min_key<uint64_t> (uint64_t
 constexpr uint32_t kSecondPassSlots = 1024;   // per-warp table of the second pass of the fused kernel
 
 template <class K>
-__host__ __device__ inline size_t fast_smem_bytes (uint32_t T) {
+__host__ __device__ inline size_t fast_smem_bytes (uint32_t T, uint32_t S = kStage) {
     // sdata[32] u64 | stage[kStage] K | hkeys[T] K | hcnt[T] u32 | hits[T/2+32] u32 | sbase[36] u32 |
     // ssec[36] u32 | chosen[32] u32 | list[T/2+32] u16
-    const size_t b = 32 * 8 + size_t(kStage) * sizeof(K) + size_t(T) * sizeof(K) + size_t(T) * 4
+    const size_t b = 32 * 8 + size_t(S) * sizeof(K) + size_t(T) * sizeof(K) + size_t(T) * 4
                    + (size_t(T) / 2 + 32) * 6 + 36 * 4 + 36 * 4 + 32 * 4;
     return (b + 15) & ~size_t(15);
 }
@@ -321,7 +321,9 @@ __device__ __forceinline__ bool agg_wave (K* hkeys, uint32_t* hcnt, uint16_t* li
 // kernels_shard.cu) instead of from the local table; everything after the aggregation is the same.
 // kPf: software pipelining of the next read (table mode): 0 none, 1 header + first features in registers and
 // the home sectors prefetched into L2, 2 the home sectors loaded into registers as well (more registers)
-template <class K, bool kLists, int kPf = 0>
+// kFilter: the single-hit filter on the staged list (table mode, merged tables); a separate instantiation so that
+// the default one keeps its 40 registers (six CTAs per SM)
+template <class K, bool kLists, int kPf = 0, bool kFilter = false>
 __global__ void __launch_bounds__(kQWarps * 32)
 query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
 {
@@ -329,10 +331,11 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     constexpr uint32_t EPS = 32 / sizeof(K);                                   // locations per 32-byte sector
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T);
+    constexpr uint32_t S = kFilter ? 2 * kStage : kStage;                      // staged locations per chunk (twice for merged tables)
+    uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T, S);
     uint64_t* sdata = reinterpret_cast<uint64_t*>(mine);                       // [32]
     K*        stage = reinterpret_cast<K*>(sdata + 32);                        // [kStage]
-    K*        hkeys = stage + kStage;                                          // [T]   (16-byte aligned)
+    K*        hkeys = stage + S;                                               // [T]   (16-byte aligned)
     uint32_t* hcnt  = reinterpret_cast<uint32_t*>(hkeys + T);                  // [T]
     uint32_t* hits  = hcnt + T;                                                // [T/2+32]
     uint32_t* sbase = hits + (T / 2 + 32);                                     // [36] first staged location per lane
@@ -492,7 +495,7 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
                     if (keep) stage[staged + __popc(km & ((1u << lane) - 1u))] = v[u];
                     staged += __popc(km);
                 }
-                if (staged > kStage - 128 || p0 + 128 >= total) {                   // flush the compacted survivors
+                if (staged > S - 128 || p0 + 128 >= total) {                        // flush the compacted survivors
                     __syncwarp();
                     for (uint32_t s0 = 0; s0 < staged && ok; s0 += 32) {
                         const uint32_t i = s0 + lane;
@@ -532,7 +535,7 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
         sbase[lane] = sb;
         sdata[lane] = data;
         if (lane == 31) sbase[32] = total;
-        if (total <= kStage) {
+        if (total <= S) {
             // dense list of the chunk's locations.  Inline buckets come out of the slot; the others
             // are fetched sector by sector (32 B), consecutive lanes taking consecutive sectors of a
             // bucket, so that a bucket costs ONE memory request per 64-byte line
@@ -568,12 +571,52 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
                 }
             }
             __syncwarp();
-            // (the single-hit filter of the lists branch was tried here for one-chunk reads - all a read finds in
-            // the parts it does not come from are single hits - and LOST: kernel 16.2 vs 15.05 ms on C2, 15.9 vs
-            // 14.4 ms per part at N=2; two more passes over the staged list cost more than the inserts they save)
-            for (uint32_t p0 = 0; p0 < total && ok; p0 += 32) {
+            // The single-hit filter of the lists branch on the staged list of a one-chunk read, for MERGED tables
+            // (all parts of a partitioned database in one table: a.filter_min != 0), where unrelated single hits
+            // are the majority of a read's locations.  (On a single part it LOSES - kernel 16.2 vs 15.05 ms on C2 -
+            // two more passes over the list cost more than the inserts they save; there it is off.)
+            uint32_t n_agg = total;
+            K g1 = AK::kEmpty, g2 = AK::kEmpty;
+            if (kFilter && a.maxc <= 2 && nslots <= 32 && total >= a.filter_min) {
+                const uint32_t fb = 31u - __clz((T / 2 + 32) / 2) + 5u;
+                uint32_t* seen = hits;
+                uint32_t* dup  = hits + (1u << (fb - 5u));
+                for (uint32_t i = lane; i < (2u << (fb - 5u)); i += 32) hits[i] = 0;
+                __syncwarp();
+                for (uint32_t p = lane; p < total; p += 32) {
+                    const uint32_t h = (AK::tgt(stage[p], wb) * 0x9E3779B1u) >> (32u - fb), bit = 1u << (h & 31u);
+                    if (atomicOr(seen + (h >> 5), bit) & bit) atomicOr(dup + (h >> 5), bit);
+                }
+                __syncwarp();
+                K m1 = AK::kEmpty, m2 = AK::kEmpty;
+                uint32_t kept = 0;
+                for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                    const uint32_t p = p0 + lane;
+                    bool keep = false;
+                    K v = AK::kEmpty;
+                    if (p < total) {
+                        v = stage[p];
+                        const uint32_t h = (AK::tgt(v, wb) * 0x9E3779B1u) >> (32u - fb);
+                        keep = (dup[h >> 5] >> (h & 31u)) & 1u;
+                        if (!keep) { if (v < m1) { m2 = m1; m1 = v; } else if (v < m2) m2 = v; }
+                    }
+                    const uint32_t km = __ballot_sync(kFull, keep);          // (every lane has read its entry by now)
+                    if (keep) stage[kept + __popc(km & ((1u << lane) - 1u))] = v;
+                    kept += __popc(km);
+                }
+                g1 = warp_min_key<K>(m1);
+                if (m1 == g1) m1 = m2;
+                g2 = warp_min_key<K>(m1);
+                n_agg = kept;
+                __syncwarp();
+            }
+            for (uint32_t p0 = 0; p0 < n_agg && ok; p0 += 32) {
                 const uint32_t p = p0 + lane;
-                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, p < total, p < total ? stage[p] : AK::kEmpty, D);
+                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, p < n_agg, p < n_agg ? stage[p] : AK::kEmpty, D);
+            }
+            if (ok && g1 != AK::kEmpty) {
+                const K mine = lane == 0 ? g1 : (lane == 1 ? g2 : AK::kEmpty);
+                ok = agg_wave<K>(hkeys, hcnt, list, mask, dmax, mine != AK::kEmpty, mine, D);
             }
         } else {
             __syncwarp();
@@ -933,6 +976,7 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
         cudaFuncSetAttribute(query_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(query_fast_kernel<uint32_t, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(query_fast_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -947,10 +991,12 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
         static const int pfmode = [] { const char* e = getenv("MCB200_PREFETCH"); return e ? atoi(e) : kDefaultPrefetch; }();
         for (int pass = 0; pass < 2; ++pass) {
             const uint32_t Tp = pass == 0 ? T : std::max<uint32_t>(T, kSecondPassSlots);
-            const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
+            const bool filter = !lists && a.table.win_bits && a.filter_min;   // the kFilter instantiation (merged tables)
+            const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp, filter ? 2 * kStage : kStage) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
             int per_sm = 0;
             if (a.table.win_bits && pfmode == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 2>, kQWarps * 32, smem);
             else if (a.table.win_bits && pfmode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 1>, kQWarps * 32, smem);
+            else if (filter) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 0, true>, kQWarps * 32, smem);
             else if (a.table.win_bits) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false>, kQWarps * 32, smem);
             else                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint64_t, false>, kQWarps * 32, smem);
             if (per_sm < 1) per_sm = 1;
@@ -964,6 +1010,8 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
                 if (a.table.win_bits) query_fast_kernel<uint32_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
                 else                  query_fast_kernel<uint64_t, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             }
+            else if (filter)
+                query_fast_kernel<uint32_t, false, 0, true><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
             else if (a.table.win_bits) {
                 if (pfmode == 2)      query_fast_kernel<uint32_t, false, 2><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
                 else if (pfmode == 1) query_fast_kernel<uint32_t, false, 1><<<pgrid, kQWarps * 32, smem, st>>>(a, Tp, in_queue, uint32_t(pass));
