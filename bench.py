@@ -55,16 +55,17 @@ def parse():
     ap.add_argument("--replicate", action="store_true",
                     help="N > 1: every GPU holds the SAME single-part database and queries only its own reads "
                          "(the reference's -replicate mode, SURVEY 8e) instead of the target-sharded database")
-    ap.add_argument("--replicate-merged", action="store_true",
-                    help="N > 1: every GPU holds ALL N parts merged into one table (buckets of a feature concatenated in "
-                         "part order; N x 14 GB fits the 180 GB of a B200 up to N = 8) and queries only its own reads: the "
-                         "N-part database without any exchange.  Not the sharded configuration BASELINE names; reported "
-                         "beside it")
-    ap.add_argument("--shard-by", default="target", choices=["feature", "target"],
-                    help="N > 1: target = the reference's own partitioning, one part per GPU, every GPU probes every read "
-                         "against its part (default: the faster mode on DB-S at every N measured); feature = every GPU owns "
-                         "a slice of the FEATURE space with the locations of all parts (one table access per feature "
-                         "however many GPUs; location lists travel back to the read's GPU)")
+    ap.add_argument("--replicate-merged", action="store_true", help="same as --shard-by merged")
+    ap.add_argument("--shard-by", default="auto", choices=["auto", "merged", "target", "feature"],
+                    help="N > 1, how the N-part database is held (DESIGN.md 5).  merged: every GPU holds ALL parts merged "
+                         "into one table (buckets of a feature concatenated in part order) and queries only ITS reads - "
+                         "reads shard, nothing is exchanged in the data path; needs the whole database in one GPU's "
+                         "180 GB.  target: the reference's partitioning, one part per GPU, every GPU probes every read, "
+                         "NCCL all-gather of sketches + all-to-all of partial top hits (the capacity mode).  feature: "
+                         "every GPU owns a slice of the feature space, features and location lists travel over NCCL.  "
+                         "auto (default): merged if the database fits, else target")
+    ap.add_argument("--no-compare-target", action="store_true",
+                    help="merged mode: skip the short target-sharded measurement reported beside it")
     ap.add_argument("--shard-streams", type=int, default=3, help="CUDA streams of the feature-sharded chunk pipeline (1 = every operation serial, for profiling)")
     ap.add_argument("--chunk-reads", type=int, default=1_250_000, help="reads per pipeline chunk of the feature-sharded step")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
@@ -296,7 +297,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     import threading
     import torch
     from metacache_b200 import _lib
-    T = max(1, min(os.cpu_count() or 1, args.e2e_threads or 32))
+    T = max(1, min((os.cpu_count() or 1) // max(1, args.gpus), args.e2e_threads or 32))    # the ranks of a box share its cores
     per = min(args.slot_reads, (nq + T - 1) // T)
     chunks = [(c, min(c + per, nq)) for c in range(0, nq, per)]
     nslots = 3 * T
@@ -496,19 +497,46 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
-    sharded = world > 1 and not args.replicate and not args.replicate_merged   # else: independent replicas (or one GPU)
+    mode = args.shard_by
+    if args.replicate_merged:
+        mode = "merged"
+    if world == 1 or args.replicate:
+        mode = "single"
+    elif mode == "auto":
+        # the sharded load keeps every part's (feature, location) pairs twice for a moment (collected + merged,
+        # 8 B per location) plus sort keys and the final table: ~26 B per location at the peak
+        need = world * (args.targets * (args.target_len / SK["winstride"]) * SK["sketchlen"]) * 26.0
+        mode = "merged" if need < 0.85 * torch.cuda.get_device_properties(device).total_memory else "target"
+    if args.workload == "C3" and mode in ("target", "feature"):
+        raise SystemExit("workload C3 with a sharded database: use --shard-by merged or --replicate for N > 1")
+    args.replicate_merged = mode == "merged"
+    args.shard_by = mode if mode in ("target", "feature") else "target"
+    sharded = mode in ("target", "feature")                  # else: every GPU answers its own reads alone
     part = rank if sharded else 0
     threads = os.cpu_count() or 1
 
     if not args.reads:
         args.reads = 10_000_000 if args.workload == "C2" else 2_000_000
-    if args.workload == "C3" and sharded:
-        raise SystemExit("workload C3 is a single-GPU configuration (BASELINE.json configs[2]); use --replicate for N > 1")
     by_feature = sharded and args.shard_by == "feature"
     if by_feature:
         db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device)
     elif args.replicate_merged and world > 1:
-        db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device, all_features=True)
+        # if the merged table does not fit on some rank, every rank falls back to the target-sharded database
+        try:
+            db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device, all_features=True)
+            ok = 1
+        except (RuntimeError, MemoryError) as ex:
+            sys.stderr.write(f"[rank {rank}] merged table not built ({type(ex).__name__}: {str(ex)[:200]}): target-sharded instead\n")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            db = bases = wins = dbinfo = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            args.replicate_merged, sharded, part = False, True, rank
+            db, bases, wins, dbinfo = build_part(args, part, device)
     else:
         db, bases, wins, dbinfo = build_part(args, part, device)
     flat, offs = make_reads(args, bases, rank, device)       # uint8 bases back to back + int64 offsets, on the device
@@ -520,8 +548,8 @@ def main():
                  f"{world}-way target-partitioned database ({world * args.targets} targets) sharded by FEATURE over "
                  f"{world} GPUs, features and location lists exchanged over NCCL" if by_feature else
                  f"{world}-way target-partitioned, one part per GPU, every GPU probes every read" if sharded else
-                 f"{world}-way target-partitioned database ({world * args.targets} targets) merged into one table and "
-                 f"replicated on {world} GPUs, every GPU queries its own reads, no exchange" if args.replicate_merged else
+                 f"{world}-way target-partitioned database ({world * args.targets} targets), all parts merged into one "
+                 f"table on every GPU, every GPU queries its own reads (no exchange in the data path)" if args.replicate_merged else
                  f"single partition replicated on {world} GPUs, every GPU queries its own reads")
     if args.workload == "C2":
         metric = "reads_per_second_150bp"

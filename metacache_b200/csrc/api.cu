@@ -459,13 +459,15 @@ extern "C" int mcb200_db_shard_finish (mcb200_db* db, uint32_t part, float max_l
     if (e == cudaSuccess) e = cudaMalloc(&sizes, std::max<uint64_t>(nrec, 1));
     if (e == cudaSuccess) e = cudaMalloc(&values, std::max<uint64_t>(nval, 1) * 8);
     uint64_t ko = 0, vo = 0;
-    for (auto& c : p.shard_chunks) {
+    for (auto& c : p.shard_chunks) {           // every batch is released as soon as it is copied (peak memory)
         if (e == cudaSuccess) e = cudaMemcpyAsync(keys + ko, c.keys, c.nkeys * 4, cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(sizes + ko, c.sizes, c.nkeys, cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess && c.nvalues) e = cudaMemcpyAsync(values + vo, c.values, c.nvalues * 8, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         ko += c.nkeys; vo += c.nvalues;
+        if (c.keys) cudaFree(c.keys); if (c.sizes) cudaFree(c.sizes); if (c.values) cudaFree(c.values);
+        c = BuiltPart{nullptr, nullptr, nullptr, 0, 0};
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     free_chunks(p);
     if (e != cudaSuccess) {
         if (keys) cudaFree(keys); if (sizes) cudaFree(sizes); if (values) cudaFree(values);

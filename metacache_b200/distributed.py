@@ -526,10 +526,24 @@ def load_feature_shard(db, shard, n_shards, n_targets, feed_parts, comm, max_loa
     mcb200_db_build_part_from_targets on slot 0).  The shards agree on one location packing."""
     import torch
     L = _lib.lib()
-    _lib.check(L.mcb200_db_shard_begin(db._h, 0, shard, n_shards, n_targets))
-    feed_parts(db)
-    mt, mw = C.c_uint32(0), C.c_uint32(0)
-    _lib.check(L.mcb200_db_shard_maxima(db._h, 0, C.byref(mt), C.byref(mw)))
     dev = torch.device("cuda", db.device) if torch.cuda.is_available() else torch.device("cpu")
-    mx = comm.all_gather_counts(torch.tensor([mt.value, mw.value], dtype=torch.int64, device=dev)).result()
-    _lib.check(L.mcb200_db_shard_finish(db._h, 0, max_load_factor, int(mx[:, 0].max()), int(mx[:, 1].max())))
+    mt, mw = C.c_uint32(0), C.c_uint32(0)
+    # a rank that fails (out of memory while collecting, say) must not leave the others waiting in a
+    # collective: every rank reports its status with the maxima, and all raise together
+    err = None
+    try:
+        _lib.check(L.mcb200_db_shard_begin(db._h, 0, shard, n_shards, n_targets))
+        feed_parts(db)
+        _lib.check(L.mcb200_db_shard_maxima(db._h, 0, C.byref(mt), C.byref(mw)))
+    except Exception as ex:                              # noqa: BLE001 - re-raised on every rank below
+        err = ex
+    mx = comm.all_gather_counts(torch.tensor([mt.value, mw.value, int(err is None)], dtype=torch.int64, device=dev)).result()
+    if err is not None or not mx[:, 2].all():
+        raise RuntimeError(f"sharded load failed on rank(s) {[int(r) for r in np.flatnonzero(mx[:, 2] == 0)]}: {err}")
+    try:
+        _lib.check(L.mcb200_db_shard_finish(db._h, 0, max_load_factor, int(mx[:, 0].max()), int(mx[:, 1].max())))
+    except Exception as ex:                              # noqa: BLE001
+        err = ex
+    okf = comm.all_gather_counts(torch.tensor([int(err is None)], dtype=torch.int64, device=dev)).result()
+    if err is not None or not okf.all():
+        raise RuntimeError(f"building the shard table failed on rank(s) {[int(r) for r in np.flatnonzero(okf[:, 0] == 0)]}: {err}")
