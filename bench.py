@@ -7,8 +7,10 @@ A "step" is one pass of the hot path (encode -> sketch -> probe -> per-read sort
 contiguous-window top hits [-> partial-top exchange + merge at N > 1]) over one batch of
 synthetic reads.  Workload at N = 1 is BASELINE config C2: 10 M x 150 bp reads (R150 recipe)
 against the 50 k-target / 16-mer synthetic database DB-S (metacache_b200/synth.py).  At N > 1
-the database is sharded by target, one part per GPU (weak scaling: every rank adds one DB-S
-sized part and 10 M reads), partial top hits are exchanged over NCCL and merged on device.
+every rank adds one DB-S sized part and 10 M reads (weak scaling).  --shard-by auto (default): all
+parts merged into one table on every GPU when that fits its 180 GB (reads shard, no exchange in the
+data path), else the reference's partitioning, one part per GPU, with partial top hits exchanged
+over NCCL and merged on device (--shard-by target); --shard-by feature: feature-space sharding.
 
 Prints ONE JSON line (see DESIGN.md "Measurement" for the fields).
 """
@@ -64,8 +66,9 @@ def parse():
                          "NCCL all-gather of sketches + all-to-all of partial top hits (the capacity mode).  feature: "
                          "every GPU owns a slice of the feature space, features and location lists travel over NCCL.  "
                          "auto (default): merged if the database fits, else target")
-    ap.add_argument("--no-compare-target", action="store_true",
-                    help="merged mode: skip the short target-sharded measurement reported beside it")
+    ap.add_argument("--merged-parts", type=int, default=0,
+                    help="merged mode: number of database parts merged on every GPU (0 = one per rank); lets one GPU "
+                         "measure the kernel on the N-part database")
     ap.add_argument("--shard-streams", type=int, default=3, help="CUDA streams of the feature-sharded chunk pipeline (1 = every operation serial, for profiling)")
     ap.add_argument("--chunk-reads", type=int, default=1_250_000, help="reads per pipeline chunk of the feature-sharded step")
     ap.add_argument("--table-slots", type=int, default=0, help="per-warp aggregation table slots (0 = library default)")
@@ -165,15 +168,19 @@ def build_feature_shard(args, rank, world, device, all_features=False):
     import torch
     from metacache_b200 import _lib, synth
     from metacache_b200.database import Database
-    from metacache_b200.distributed import TorchComm, load_feature_shard
+    from metacache_b200.distributed import ThreadComm, TorchComm, load_feature_shard
     from metacache_b200._lib import Sketching
     t0 = time.time()
+    nparts = max(world, args.merged_parts) if all_features else world
+    comm = TorchComm() if world > 1 else ThreadComm(ThreadComm.Shared(1), 0)
+    # the merged table is built with room to spare (180 GB): short probe sequences
+    lf = args.load_factor or (0.3 if all_features else 0.0)
     db = Database(device.index, 1)
     sk = Sketching(**SK)
     keep = {}
 
     def feed(d):
-        for p in range(world):
+        for p in range(nparts):
             bases, off = synth.make_targets(args.targets, args.target_len, 10, synth.SEED_DB + p, device=device)
             wins = np.zeros(args.targets, np.uint32)
             _lib.check(_lib.lib().mcb200_db_build_part_from_targets(
@@ -185,12 +192,12 @@ def build_feature_shard(args, rank, world, device, all_features=False):
             torch.cuda.empty_cache()
 
     # all_features: "shard 0 of 1" = every feature, i.e. the whole N-part database merged on this GPU
-    load_feature_shard(db, 0 if all_features else rank, 1 if all_features else world, world * args.targets, feed,
-                       TorchComm(), args.load_factor)
+    load_feature_shard(db, 0 if all_features else rank, 1 if all_features else world, nparts * args.targets, feed,
+                       comm, lf)
     torch.cuda.synchronize(device)
     info = dict(build_s=round(time.time() - t0, 2), keys=db.key_count(0), locations=db.value_count(0),
                 table_gb=round(db.device_bytes(0) / 1e9, 2),
-                shard=("all %d parts merged on every GPU" if all_features else "features of all %d parts owned by this rank") % world)
+                shard=("all %d parts merged on every GPU" if all_features else "features of all %d parts owned by this rank") % nparts)
     return db, keep["bases"], keep["wins"], info
 
 
@@ -500,7 +507,9 @@ def main():
     mode = args.shard_by
     if args.replicate_merged:
         mode = "merged"
-    if world == 1 or args.replicate:
+    if args.merged_parts > 1:
+        mode = "merged"
+    elif world == 1 or args.replicate:
         mode = "single"
     elif mode == "auto":
         # the sharded load keeps every part's (feature, location) pairs twice for a moment (collected + merged,
@@ -520,7 +529,9 @@ def main():
     by_feature = sharded and args.shard_by == "feature"
     if by_feature:
         db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device)
-    elif args.replicate_merged and world > 1:
+    elif args.replicate_merged and world == 1:
+        db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device, all_features=True)
+    elif args.replicate_merged:
         # if the merged table does not fit on some rank, every rank falls back to the target-sharded database
         try:
             db, bases, wins, dbinfo = build_feature_shard(args, rank, world, device, all_features=True)

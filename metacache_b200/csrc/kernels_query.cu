@@ -331,7 +331,7 @@ query_fast_kernel (QueryArgs a, uint32_t T, int in_queue, uint32_t out_queue)
     constexpr uint32_t EPS = 32 / sizeof(K);                                   // locations per 32-byte sector
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    constexpr uint32_t S = kFilter ? 2 * kStage : kStage;                      // staged locations per chunk (twice for merged tables)
+    constexpr uint32_t S = kFilter ? 3 * kStage : kStage;                      // staged locations per chunk (768 for merged tables: still 4 CTAs/SM)
     uint8_t* mine = smem_raw + warp * fast_smem_bytes<K>(T, S);
     uint64_t* sdata = reinterpret_cast<uint64_t*>(mine);                       // [32]
     K*        stage = reinterpret_cast<K*>(sdata + 32);                        // [kStage]
@@ -992,7 +992,7 @@ static void launch_query_warp_impl (const QueryArgs& a, uint32_t T, int sm_count
         for (int pass = 0; pass < 2; ++pass) {
             const uint32_t Tp = pass == 0 ? T : std::max<uint32_t>(T, kSecondPassSlots);
             const bool filter = !lists && a.table.win_bits && a.filter_min;   // the kFilter instantiation (merged tables)
-            const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp, filter ? 2 * kStage : kStage) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
+            const size_t smem = (a.table.win_bits ? fast_smem_bytes<uint32_t>(Tp, filter ? 3 * kStage : kStage) : fast_smem_bytes<uint64_t>(Tp)) * kQWarps;
             int per_sm = 0;
             if (a.table.win_bits && pfmode == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 2>, kQWarps * 32, smem);
             else if (a.table.win_bits && pfmode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_fast_kernel<uint32_t, false, 1>, kQWarps * 32, smem);
