@@ -424,6 +424,24 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                    "ASCII buffers to candidates in host memory (query_batch seam)"}
 
 
+def choose_shard_mode(args, world, device_bytes):
+    """How the N-part database is held at N > 1: "single" (one GPU / replicas of one part),
+    "merged" (all parts in one table on every GPU, reads sharded), "target" or "feature" (database sharded)."""
+    mode = args.shard_by
+    if args.replicate_merged:
+        mode = "merged"
+    if args.merged_parts > 1:
+        return "merged"
+    if world == 1 or args.replicate:
+        return "single"
+    if mode == "auto":
+        # the sharded load keeps every part's (feature, location) pairs twice for a moment (collected + merged,
+        # 8 B per location) plus sort keys and the final table: ~26 B per location at the peak
+        need = world * (args.targets * (args.target_len / SK["winstride"]) * SK["sketchlen"]) * 26.0
+        mode = "merged" if need < 0.85 * device_bytes else "target"
+    return mode
+
+
 def reference_sample(args, nq, threads, per_read_scale):
     return args.cpu_sample or int(min(nq, max(200_000, 150_000 * threads) * per_read_scale))
 
@@ -504,18 +522,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
-    mode = args.shard_by
-    if args.replicate_merged:
-        mode = "merged"
-    if args.merged_parts > 1:
-        mode = "merged"
-    elif world == 1 or args.replicate:
-        mode = "single"
-    elif mode == "auto":
-        # the sharded load keeps every part's (feature, location) pairs twice for a moment (collected + merged,
-        # 8 B per location) plus sort keys and the final table: ~26 B per location at the peak
-        need = world * (args.targets * (args.target_len / SK["winstride"]) * SK["sketchlen"]) * 26.0
-        mode = "merged" if need < 0.85 * torch.cuda.get_device_properties(device).total_memory else "target"
+    mode = choose_shard_mode(args, world, torch.cuda.get_device_properties(device).total_memory)
     if args.workload == "C3" and mode in ("target", "feature"):
         raise SystemExit("workload C3 with a sharded database: use --shard-by merged or --replicate for N > 1")
     args.replicate_merged = mode == "merged"
@@ -762,6 +769,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e["ms_per_step"] = round(float(t[0].item()), 3)
             e2e["value"] = nq_total / (e2e["ms_per_step"] * 1e-3)
+            e2e["prefilled"]["ms_per_step"] = round(float(t[1].item()), 3)
+            e2e["prefilled"]["value"] = nq_total / (float(t[1].item()) * 1e-3)
             e2e["h2d_bytes_per_step"] *= world
             e2e["d2h_bytes_per_step"] *= world
     else:

@@ -58,3 +58,23 @@ def test_committed_bench_lines_follow_the_contract():
             d = json.load(open(os.path.join(prof, f)))
             assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference"
             assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_shard_mode_follows_the_memory_of_the_gpu():
+    """--shard-by auto: all parts merged on every GPU while the N-part database fits one B200, else the
+    target-sharded capacity mode (BASELINE config C5 as specified: 8 x 1.5 G locations)"""
+    import argparse
+    b200 = 178 * 2 ** 30
+
+    def args(**kw):
+        d = dict(shard_by="auto", replicate_merged=False, merged_parts=0, replicate=False, targets=50_000, target_len=100_000)
+        d.update(kw)
+        return argparse.Namespace(**d)
+    assert bench.choose_shard_mode(args(), 1, b200) == "single"
+    assert [bench.choose_shard_mode(args(), n, b200) for n in (2, 4, 8)] == ["merged"] * 3
+    assert bench.choose_shard_mode(args(targets=105_000), 8, b200) == "target"          # C5 does not fit merged
+    assert bench.choose_shard_mode(args(), 8, 80 * 2 ** 30) == "target"                 # a smaller GPU
+    assert bench.choose_shard_mode(args(shard_by="target"), 4, b200) == "target"
+    assert bench.choose_shard_mode(args(shard_by="feature"), 4, b200) == "feature"
+    assert bench.choose_shard_mode(args(replicate=True), 4, b200) == "single"
+    assert bench.choose_shard_mode(args(merged_parts=8), 1, b200) == "merged"
