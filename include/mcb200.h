@@ -315,9 +315,11 @@ int mcb200_query_packed_device (mcb200_workspace* ws, const mcb200_dev_queries* 
  * part order, so on equal hits a target of an earlier part wins whatever its id;
  * the shard learns each target's part from the locations it is fed and numbers
  * targets part-major internally (candidates come back with the original ids).
- * n_targets = 0 skips that: ids must then ascend with the part.  All shards must pack
+ * n_targets = 0 skips that: ids must then ascend with the part; MCB200_TARGETS_AUTO
+ * lets the shard size the map by the largest id it is fed.  All shards must pack
  * locations alike: pass the database-wide largest target and window id (each
  * shard's own maxima from shard_maxima, reduced with max over the shards).       */
+#define MCB200_TARGETS_AUTO 0xFFFFFFFFu
 int mcb200_db_shard_begin  (mcb200_db* db, uint32_t part, uint32_t shard, uint32_t n_shards,
                             uint32_t n_targets);
 int mcb200_db_shard_maxima (mcb200_db* db, uint32_t part, uint32_t* max_target_id, uint32_t* max_window_id);

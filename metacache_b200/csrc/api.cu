@@ -104,6 +104,7 @@ struct Part {
     // learnt from the locations of every source part, tgt_orig translates candidates back (null = identity).
     uint8_t*  d_part_of = nullptr;
     uint32_t  n_targets = 0;
+    bool      grow_targets = false;          // n_targets learnt from the locations fed (MCB200_TARGETS_AUTO)
     int       src_part = -1;
     uint32_t* d_tgt_orig = nullptr;
 };
@@ -331,6 +332,21 @@ __global__ void translate_targets_kernel (mcb200_candidate* __restrict__ top, ui
 
 static int shard_collect (mcb200_db* db, Part& p, const uint32_t* d_keys, const uint8_t* d_sizes,
                           const uint64_t* d_values, uint64_t nkeys, uint64_t nvalues) {
+    if (p.grow_targets && nvalues) {
+        // number of targets not declared: make room for the largest id of this batch
+        uint32_t m[2] = {0, 0};
+        if (device_loc_max(d_values, nvalues, m, db->stream) != 0)
+            return fail(MCB200_ECUDA, "sharded load: scanning the locations failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (m[0] >= p.n_targets) {
+            const uint32_t want = std::max<uint32_t>(m[0] + 1, p.n_targets + p.n_targets / 2 + 1024);
+            uint8_t* bigger = nullptr;
+            CU(cudaMalloc(&bigger, want));
+            CU(cudaMemsetAsync(bigger, 0xFF, want, db->stream));
+            if (p.d_part_of) { CU(cudaMemcpyAsync(bigger, p.d_part_of, p.n_targets, cudaMemcpyDeviceToDevice, db->stream));
+                               CU(cudaStreamSynchronize(db->stream)); cudaFree(p.d_part_of); }
+            p.d_part_of = bigger; p.n_targets = want;
+        }
+    }
     if (p.d_part_of && nvalues) {
         mark_parts_kernel<<<unsigned((nvalues + 255) / 256), 256, 0, db->stream>>>(
             d_values, nvalues, p.d_part_of, p.n_targets, uint8_t(std::max(p.src_part, 0)), db->d_error);
@@ -434,7 +450,10 @@ extern "C" int mcb200_db_shard_begin (mcb200_db* db, uint32_t part, uint32_t sha
     Part& p = db->parts[part];
     free_part(p);
     p.shard_mode = true; p.shard = shard; p.n_shards = n_shards;
-    if (n_targets) {
+    if (n_targets == 0xFFFFFFFFu) {
+        p.grow_targets = true;
+        CU(cudaMemsetAsync(db->d_error, 0, sizeof(int), db->stream));
+    } else if (n_targets) {
         CU(cudaMalloc(&p.d_part_of, n_targets));
         CU(cudaMemsetAsync(p.d_part_of, 0xFF, n_targets, db->stream));
         CU(cudaMemsetAsync(db->d_error, 0, sizeof(int), db->stream));

@@ -37,6 +37,7 @@
 #include <vector>
 #include <thread>
 #include <mutex>
+#include <condition_variable>
 #include <fstream>
 #include <exception>
 #include <cstdlib>
@@ -150,7 +151,7 @@ public:
     gpu_hashmap (const gpu_hashmap&) = delete;
     gpu_hashmap (gpu_hashmap&& o) noexcept
         : device_(o.device_), db_(o.db_), maxLoadFactor_(o.maxLoadFactor_), maxLoc_(o.maxLoc_),
-          lineages_(std::move(o.lineages_)), taxRank_(o.taxRank_)
+          mergedParts_(o.mergedParts_), partsRead_(o.partsRead_), lineages_(std::move(o.lineages_)), taxRank_(o.taxRank_)
     { o.db_ = nullptr; if (current() == &o) current() = this; }
     ~gpu_hashmap () { if (db_) mcb200_db_close(db_); if (current() == this) current() = nullptr; }
     static int default_device () { const char* e = std::getenv("MCB200_DEVICE"); return e ? std::atoi(e) : 0; }
@@ -161,6 +162,19 @@ public:
     //--- query tables (gpu_hashmap.cu:1320-1362) ---
     void prepare_query_tables (part_id numParts, unsigned /*replication*/ = 1) {
         if (db_) mcb200_db_close(db_);
+        mergedParts_ = 0; partsRead_ = 0;
+        // MCB200_MERGE_PARTS=1: all parts of a multi-part database in ONE table on one GPU (buckets of a feature
+        // concatenated in part order: one table access per feature however many parts; results are those of
+        // the per-part query + part-ordered merge).  The parts must then be read in ascending order.
+        const char* mp = std::getenv("MCB200_MERGE_PARTS");
+        if (numParts > 1 && mp && std::atoi(mp) != 0) {
+            db_ = mcb200_db_open(device_, 1);
+            if (!db_) throw_last("prepare_query_tables");
+            if (mcb200_db_shard_begin(db_, 0, 0, 1, MCB200_TARGETS_AUTO)) throw_last("prepare_query_tables");
+            mergedParts_ = numParts;
+            current() = this;
+            return;
+        }
         // one part per GPU like the reference (gpu_hashmap.cuh:116-130) when the box has enough devices;
         // MCB200_DEVICES="0,1,.." names the device of every part explicitly (cycled), a single entry = one GPU
         std::vector<int> devs;
@@ -175,8 +189,9 @@ public:
         if (!db_) throw_last("prepare_query_tables");
         current() = this;
     }
-    part_id table_count () const noexcept { return db_ ? part_id(mcb200_db_part_count(db_)) : 0; }
+    part_id table_count () const noexcept { return mergedParts_ ? mergedParts_ : (db_ ? part_id(mcb200_db_part_count(db_)) : 0); }
     part_id gpu_count () const noexcept {
+        if (mergedParts_) return 1;
         std::vector<int> seen;
         for (part_id p = 0; db_ && p < table_count(); ++p) {
             const int d = mcb200_db_part_device(db_, p);
@@ -199,6 +214,18 @@ public:
     template <class Progress>
     void deserialize (std::istream& is, part_id partId, Progress& progress) {
         gpu_hashmap& m = *this;
+        // the reference reads the parts with one thread each (database.cpp:207-215); the store loads one at a
+        // time, and in ascending order when the parts are merged into one table
+        std::unique_lock<std::mutex> lock(load_mutex());
+        if (m.mergedParts_) {                       // every part goes through slot 0 of the collecting store
+            load_turn().wait(lock, [&] { return m.partsRead_ == partId || m.partsRead_ > m.mergedParts_; });
+            if (m.partsRead_ > m.mergedParts_) throw std::runtime_error("MCB200_MERGE_PARTS: an earlier database part failed to load");
+            partId = 0;
+        }
+        struct Poison {     // a failure below must not leave the readers of the later parts waiting
+            gpu_hashmap& m; bool armed;
+            ~Poison () { if (armed && m.mergedParts_) { m.partsRead_ = m.mergedParts_ + 1; load_turn().notify_all(); } }
+        } poison{m, true};
         std::uint64_t hdr[3];
         is.read(reinterpret_cast<char*>(hdr), sizeof hdr);
         if (!is) throw std::runtime_error("could not read database part header");
@@ -220,7 +247,18 @@ public:
             advance(progress, b, nkeys, done);
         }
         if (mcb200_db_part_finish(m.db_, partId)) throw_last("read_binary");
+        if (m.mergedParts_) {
+            if (++m.partsRead_ == m.mergedParts_) {
+                std::uint32_t mt = 0, mw = 0;
+                if (mcb200_db_shard_maxima(m.db_, 0, &mt, &mw) || mcb200_db_shard_finish(m.db_, 0, m.maxLoadFactor_, mt, mw))
+                    throw_last("read_binary (merging the parts)");
+            }
+            load_turn().notify_all();
+        }
+        poison.armed = false;
     }
+    static std::mutex& load_mutex () { static std::mutex m; return m; }
+    static std::condition_variable& load_turn () { static std::condition_variable c; return c; }
 
     /** copy_target_lineages_to_gpus (gpu_hashmap.cuh): kept on the host for `tax` pointers;
      *  the device gets the per-target key at the rank given to query_async */
@@ -292,6 +330,7 @@ private:
     mcb200_db* db_ = nullptr;
     float maxLoadFactor_ = 0.f;
     bucket_size_type maxLoc_ = 254;
+    part_id mergedParts_ = 0, partsRead_ = 0;   // MCB200_MERGE_PARTS: parts of the database / read so far
     std::vector<ranked_lineage> lineages_;
     mutable int taxRank_ = 0;            // rank whose keys are on the device (0 = sequence: none needed)
     friend class query_batch<ValueT>;

@@ -168,3 +168,32 @@ def test_all_parts_merged_into_one_table_equal_the_reference_per_part_merge():
     bad = [i for i, (_, top) in enumerate(res) if top != want[i]]
     assert not bad, (bad[:5], res[bad[0]][1], want[bad[0]])
     db.close()
+
+
+def test_cpp_shim_merges_the_parts_of_a_database_into_one_table(tmp_path):
+    """MCB200_MERGE_PARTS=1: host/shim_query (database_query.hpp:87-124 on the shim) loads the two `.cache`
+    files of golden g2 into ONE merged table on one GPU; the target map is sized from the locations
+    (MCB200_TARGETS_AUTO); results = the reference's per-part outputs merged in part order"""
+    import os
+    import subprocess
+    from metacache_b200 import dbformat
+    from oracle import refio
+    g1, g2 = G1(), G2()
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(here, "..", "metacache_b200", "host", "shim_query")
+    assert os.path.exists(exe), "run build() first"
+    base = str(tmp_path / "g2")
+    for p in (0, 1):
+        dbformat.write_cache(f"{base}.cache{p}", dbformat.CachePart(*g2.parts[p]))
+    rt = str(tmp_path / "reads.txt")
+    norm = lambda x: x if len(x) else b"-"
+    refio.write_reads_txt(rt, [(norm(a), norm(b)) if len(b) else norm(a) for a, b in g1.reads])
+    env = dict(os.environ, MCB200_MERGE_PARTS="1")
+    out = subprocess.run([exe, base, rt, "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-1500:]
+    rows = [ln for ln in out.stdout.splitlines() if not ln.startswith("#")]
+    assert "# parts=2 devices=1" in out.stdout and len(rows) == len(g1.reads)
+    want = _expected(len(g1.reads))
+    for i, ln in enumerate(rows):
+        got = [tuple(int(x) for x in c.split(":")) for c in ln.split("\t")[1].split(",") if c]
+        assert got == want[i], i
