@@ -24,6 +24,7 @@ REF_SAMPLE = 2_000_000
 
 class A:
     targets, target_len, load_factor, reads, workload = 50_000, 100_000, 0.0, NQ, "C2"
+    replicate_merged, merged_parts = False, 0
     cache = "/dev/shm/mcb200_bench"
 
 
@@ -87,6 +88,19 @@ if os.path.exists(ref_bin):
     lines = [l.strip() for l in p.stdout.replace("\r", "\n").splitlines()
              if l.startswith("# queries") or l.startswith("# time") or l.startswith("# speed")]
     out["reference_cli"] = {"threads": threads, "reads": REF_SAMPLE, "wall_s_incl_db_load": round(dt, 1), "reported": lines}
+    # the same CLI built on libmcb200 (oracle/_ref/metacache_mcb200: the reference's host program, unchanged,
+    # with the two seam headers replaced - INTEGRATION.md 1): same sample, then the whole file
+    dropin = os.path.join(ROOT, "oracle", "_ref", "metacache_mcb200")
+    if os.path.exists(dropin):
+        for name, fpath, nreads in (("dropin_cli_sample", sample, REF_SAMPLE), ("dropin_cli_full_file", path, NQ)):
+            t0 = time.time()
+            p = subprocess.run([dropin, "query", base, fpath, "-threads", str(threads), "-no-map"],
+                               capture_output=True, text=True)
+            dt = time.time() - t0
+            lines = [l.strip() for l in p.stdout.replace("\r", "\n").splitlines()
+                     if l.startswith("# queries") or l.startswith("# time") or l.startswith("# speed")]
+            out[name] = {"threads": threads, "reads": nreads, "wall_s_incl_db_load": round(dt, 1), "reported": lines,
+                         "rc": p.returncode, "stderr_tail": p.stderr[-200:] if p.returncode else ""}
     os.unlink(sample)
 os.unlink(path)
 print(json.dumps(out))
