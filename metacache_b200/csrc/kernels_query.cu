@@ -32,7 +32,10 @@
 
 namespace mcb {
 
-constexpr int      kQWarps   = 8;           // warps per CTA in the fused kernel
+#ifndef MCB_QWARPS
+#define MCB_QWARPS 8
+#endif
+constexpr int      kQWarps   = MCB_QWARPS;  // warps per CTA in the fused kernel (measured: 4 = equal; 16 = 1 % faster on C2 but the 1 024-slot pass no longer fits shared memory)
 constexpr uint32_t kMaxCand  = 32;          // candidates per query supported on device
 constexpr uint32_t kCounterSlots = 64;      // counters are spread over 64 slots x 8
 
