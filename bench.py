@@ -66,6 +66,8 @@ def parse():
                          "NCCL all-gather of sketches + all-to-all of partial top hits (the capacity mode).  feature: "
                          "every GPU owns a slice of the feature space, features and location lists travel over NCCL.  "
                          "auto (default): merged if the database fits, else target")
+    ap.add_argument("--no-compare-target", action="store_true",
+                    help="merged mode at N > 1: skip the short target-sharded measurement reported beside it")
     ap.add_argument("--merged-parts", type=int, default=0,
                     help="merged mode: number of database parts merged on every GPU (0 = one per rank); lets one GPU "
                          "measure the kernel on the N-part database")
@@ -422,6 +424,60 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
                                   "CUDA events across the slots' streams, scaled from %d reads" % pre_reads},
             "api": "mcb200_batch_add_reads (packs 2 bit/base on the host) + submit + wait, from the caller's "
                    "ASCII buffers to candidates in host memory (query_batch seam)"}
+
+
+def compare_target_sharded(args, rank, world, device, stream, nq, n_bases, SK_, maxc, dist, barrier):
+    """The reference's partitioning on the same reads, in the same run: rank r holds part r, NCCL all-gather of
+    sketches, every GPU probes every read, all-to-all of partial top hits, on-device merge.
+    Short (2 warm-up + 3 timed steps); device-resident; returned for the bench line next to the merged mode."""
+    import torch
+    from metacache_b200 import _lib
+    from metacache_b200._lib import DevQueries, Sketching
+    from metacache_b200.distributed import ShardedQuery
+    L = _lib.lib()
+    # everything that can fail on one rank alone (allocations) happens before the first collective, and the
+    # ranks agree to go on: a rank that gave up must not leave the others waiting in an all-gather
+    err = None
+    try:
+        db, bases, _, info = build_part(args, rank, device)
+        flat, offs = make_reads(args, bases, rank, device)
+        del bases
+        sk = Sketching(**SK_)
+        seq_off = offs.to(torch.int32)
+        seq_qry = torch.arange(nq, dtype=torch.int32, device=device)
+        max_win = (2 + (offs[1:] - offs[:-1]) // SK_["winstride"]).to(torch.int32)
+        ws = _lib.check_ptr(L.mcb200_workspace_create(db._h, nq, nq, n_bases + 64, maxc, 0))
+        q = DevQueries(flat.data_ptr(), seq_off.data_ptr(), seq_qry.data_ptr(), max_win.data_ptr(), nq, nq, n_bases)
+        sq = ShardedQuery(db, ws, nq, 2 * nq, SK_["sketchlen"], maxc, device, stream)
+        torch.cuda.synchronize(device)
+    except Exception as ex:                                  # noqa: BLE001
+        err = ex
+    flag = torch.tensor([int(err is None)], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not int(flag.item()):
+        return {"value": None, "error": f"setup failed on a rank: {type(err).__name__ if err else 'other rank'}: {str(err)[:160] if err else ''}"}
+    try:
+        for _ in range(2):
+            sq.step(q, sk, max_win)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        steps = 3
+        for _ in range(steps):
+            sq.step(q, sk, max_win)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / steps
+        _lib.check(L.mcb200_workspace_check(ws))
+        L.mcb200_workspace_destroy(ws)
+        db.close()
+        return {"value": nq * world / (ms * 1e-3), "unit": "reads/s", "ms_per_step": round(ms, 3), "steps": steps,
+                "what": "one part per GPU, every GPU probes every read, NCCL all-gather of sketches + all-to-all of "
+                        "partial top hits + on-device merge (--shard-by target), device-resident"}
+    except Exception as ex:                                  # never lose the main numbers
+        return {"value": None, "error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
 
 def choose_shard_mode(args, world, device_bytes):
@@ -804,6 +860,11 @@ def main():
 
     clk = clocks.stop()                                      # sampled through both timed regions (value and e2e)
 
+    # ---------------- merged mode: the target-sharded step measured beside it, same run, same reads ---------
+    target_cmp = None
+    if args.replicate_merged and world > 1 and dist is not None and not args.no_compare_target and args.workload == "C2":
+        target_cmp = compare_target_sharded(args, rank, world, device, stream, nq, n_bases, SK, MAXC, dist, barrier)
+
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
     parity = None
@@ -836,6 +897,8 @@ def main():
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64", "data": "synthetic", "config": config,
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+        if target_cmp is not None:
+            out["target_sharded_same_run"] = target_cmp
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
