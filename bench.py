@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = 10 M for C2, 2 M for C3)")
     ap.add_argument("--targets", type=int, default=50_000, help="targets per database part")
     ap.add_argument("--target-len", type=int, default=100_000)
-    ap.add_argument("--slot-reads", type=int, default=250_000, help="reads per host batch slot (e2e)")
+    ap.add_argument("--slot-reads", type=int, default=125_000, help="reads per host batch slot (e2e)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host worker threads of the e2e run (0 = one per core, max 32)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -290,6 +290,20 @@ def cpu_port_run(db, flat_np, offs_np):
     return time.time() - t0
 
 
+def host_info():
+    """what the host-bound figures ran on: CPU model and usable threads (the e2e step is bound by how fast
+    the host cores read ASCII bases)"""
+    model = None
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "threads": os.cpu_count()}
+
+
 def host_sample(flat, offs, n):
     """first n reads as host arrays (bases, offsets starting at 0)"""
     o = offs[:n + 1].cpu().numpy()
@@ -300,9 +314,9 @@ def host_sample(flat, offs, n):
 def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, device):
     """End to end through the query_batch seam, from the CALLER'S host buffers to candidates in host
     memory: worker threads (one per host core, three slots each, as the reference's query workers own one
-    query_batch host slot each, database_query.hpp:87-124) add their share of the reads - which packs
-    the bases to 2 bits + ambiguity bit into the slot's pinned buffers -, submit (H2D + kernels + D2H on
-    the slot's stream) and wait.  Timed by wall clock over K back-to-back steps, host work included."""
+    query_batch host slot each, database_query.hpp:87-124) take the next chunk of reads that is due, add it -
+    which packs the bases to 2 bits + ambiguity bit into the slot's pinned buffers -, submit (H2D + kernels +
+    D2H on the slot's stream) and wait.  Timed by wall clock over K back-to-back steps, host work included."""
     import threading
     import torch
     from metacache_b200 import _lib
@@ -332,31 +346,36 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
             src = L.mcb200_batch_top_candidates(qb, slot, 0)
             C.memmove(tops[b:e].ctypes.data, src, (e - b) * MAXC * 16)
 
-    def worker(t, steps, start):
+    def worker(t, steps, start, take):
         try:
-            mine = list(range(t, len(chunks), T))
             pending = [None] * SPW
             k = 0
             start.wait()
-            for _ in range(steps):
-                for ci in mine:
-                    j = k % SPW
-                    slot = SPW * t + j
-                    t0 = time.perf_counter()
-                    if pending[j] is not None:
-                        collect(slot, pending[j])
-                    _lib.check(L.mcb200_batch_clear(qb, slot))
-                    t1 = time.perf_counter()
-                    b, e = chunks[ci]
-                    added = _lib.check(L.mcb200_batch_add_reads(qb, slot, base_ptr + int(host_offs[b]),
-                                                                chunk_offs[ci].ctypes.data, e - b, 0, 0, SK["winstride"]))
-                    assert added == e - b
-                    t2 = time.perf_counter()
-                    _lib.check(L.mcb200_batch_submit(qb, slot, C.byref(sk)))
-                    t3 = time.perf_counter()
-                    spent[t][0] += t1 - t0; spent[t][1] += t2 - t1; spent[t][2] += t3 - t2
-                    pending[j] = ci
-                    k += 1
+            while True:
+                # the next chunk of the job, whichever worker is free: K steps x len(chunks) chunks back to back
+                # (a static split leaves half the workers idle for a third of the step when the chunks do not
+                # divide by the workers: 40 chunks on 16 threads cost 3 rounds instead of 2.5)
+                n = take()
+                if n >= steps * len(chunks):
+                    break
+                ci = n % len(chunks)
+                j = k % SPW
+                slot = SPW * t + j
+                t0 = time.perf_counter()
+                if pending[j] is not None:
+                    collect(slot, pending[j])
+                _lib.check(L.mcb200_batch_clear(qb, slot))
+                t1 = time.perf_counter()
+                b, e = chunks[ci]
+                added = _lib.check(L.mcb200_batch_add_reads(qb, slot, base_ptr + int(host_offs[b]),
+                                                            chunk_offs[ci].ctypes.data, e - b, 0, 0, SK["winstride"]))
+                assert added == e - b
+                t2 = time.perf_counter()
+                _lib.check(L.mcb200_batch_submit(qb, slot, C.byref(sk)))
+                t3 = time.perf_counter()
+                spent[t][0] += t1 - t0; spent[t][1] += t2 - t1; spent[t][2] += t3 - t2
+                pending[j] = ci
+                k += 1
             t0 = time.perf_counter()
             for i in range(SPW):
                 j = (k + i) % SPW
@@ -370,7 +389,13 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
         for x in spent:
             x[:] = [0.0, 0.0, 0.0]
         start = threading.Barrier(T + 1)
-        th = [threading.Thread(target=worker, args=(t, steps, start)) for t in range(T)]
+        ticket, lock = [0], threading.Lock()
+
+        def take():
+            with lock:
+                ticket[0] += 1
+                return ticket[0] - 1
+        th = [threading.Thread(target=worker, args=(t, steps, start, take)) for t in range(T)]
         for x in th:
             x.start()
         torch.cuda.synchronize(device)
@@ -418,6 +443,8 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     return {"value": nq / (wall_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": round(wall_ms, 3), "timed_by": "wall clock, host work included",
             "host_threads": T, "slots": nslots, "reads_per_slot": per, "host_ms_per_thread_per_step": host_ms,
+            "chunks": "taken one by one by whichever worker is free",
+            "packer": ("scalar", "avx2", "avx512")[int(L.mcb200_internal_pack_has_avx2())],
             "results_equal_device_resident_path": same,
             "prefilled": {"value": nq / (pre_ms * 1e-3), "ms_per_step": round(pre_ms, 3),
                           "note": "slots filled (packed) before the timed region: pinned -> H2D -> kernels -> D2H only, "
@@ -549,7 +576,7 @@ def reference_arm(args):
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64",
                       "data": "synthetic", "config": config,
                       "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": kind,
-                                       "sample": sample_desc},
+                                       "sample": sample_desc, "host": host_info()},
                       "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 
@@ -897,6 +924,7 @@ def main():
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64", "data": "synthetic", "config": config,
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+        out["host"] = host_info()
         if target_cmp is not None:
             out["target_sharded_same_run"] = target_cmp
         print(json.dumps(out))

@@ -13,7 +13,8 @@
 // read may start at any bit offset.  Words are completed by later appends: an append ORs into the
 // partially filled word it starts in and STORES every further word (tail bits zero), which needs
 // no pre-cleared memory.  AVX-512 (F+BW) or AVX2 when the CPU has them (runtime dispatch), scalar otherwise;
-// one core packs ~8.6 GB/s of ASCII with AVX-512 (its memory read rate), ~5 GB/s with AVX2.
+// with AVX-512 one core packs ~23 GB/s of ASCII from its cache and ~9 GB/s from memory (the source is
+// prefetched in software, see kPrefetchAhead), ~12 / ~7 GB/s with AVX2.
 #include <cstdint>
 #include <cstring>
 
@@ -40,36 +41,41 @@ inline void pack32_scalar (const uint8_t* s, uint32_t n, uint64_t& codes, uint32
 }
 
 #ifdef MCB_X86
+// how far ahead of the loads the source is prefetched: the loop is a pure stream, and under a hypervisor
+// the hardware prefetchers alone leave a core at a third of its read rate (measured: 3.8 -> 9.3 GB/s per
+// core, 17 -> 45 GB/s on 8 cores; 1.5 - 2 KB ahead is the flat optimum)
+constexpr uint64_t kPrefetchAhead = 1536;
+
+// The vector paths reverse the bytes of every 16-byte lane FIRST.  The multiply-adds then leave "first base
+// in the top bits" words in place (no byte shuffle afterwards), and the validity mask needs a 16-bit rotate
+// instead of a bit reversal.  Validity and code both come from one table lookup by the low nibble of the
+// case-folded character: A=1 C=3 T=4 U=5 G=7 (an index byte with bit 7 set yields 0, which never equals it).
+#define MCB_PACK_TABLES(BCAST)                                                                               \
+    const char X = 0x20;   /* has the bit the case fold cleared: never equal to a folded character */        \
+    const auto rev = BCAST(_mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0));             \
+    const auto tbl = BCAST(_mm_setr_epi8(X, 'A', X, 'C', 'T', 'U', X, 'G', X, X, X, X, X, X, X, X));         \
+    const auto ctb = BCAST(_mm_setr_epi8(0, 0, 0, 1, 3, 3, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0))
+
 __attribute__((target("avx2")))
 inline void pack32_avx2 (const uint8_t* s, uint64_t& codes, uint32_t& amb) {
+    MCB_PACK_TABLES(_mm256_broadcastsi128_si256);
     const __m256i x  = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
-    const __m256i up = _mm256_and_si256(x, _mm256_set1_epi8(char(0xDF)));
-    // valid letters by their low nibble: A=1 C=3 T=4 U=5 G=7
-    // (0x20 has the bit the case fold cleared, so the unused entries never compare equal)
-    const char X = 0x20;
-    const __m256i tbl = _mm256_setr_epi8(X, 'A', X, 'C', 'T', 'U', X, 'G', X, X, X, X, X, X, X, X,
-                                         X, 'A', X, 'C', 'T', 'U', X, 'G', X, X, X, X, X, X, X, X);
-    const __m256i expect = _mm256_shuffle_epi8(tbl, _mm256_and_si256(up, _mm256_set1_epi8(0x0F)));
-    const __m256i ok = _mm256_cmpeq_epi8(expect, up);              
-    // (c >> 1) & 3 -> A0 C1 T2 G3 ; v ^ (v >> 1) -> A0 C1 G2 T3
-    const __m256i v  = _mm256_and_si256(_mm256_srli_epi16(up, 1), _mm256_set1_epi8(3));
-    __m256i code     = _mm256_xor_si256(v, _mm256_and_si256(_mm256_srli_epi16(v, 1), _mm256_set1_epi8(1)));
-    code = _mm256_and_si256(code, ok);
-    // 4 codes -> 1 byte, first base in the top bits
-    const __m256i p2 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0104));      // b0*4 + b1
-    const __m256i p4 = _mm256_madd_epi16(p2, _mm256_set1_epi32(0x00010010));       // lo*16 + hi
-    // byte 0 of every dword, reversed inside each 128-bit lane: little-endian u32 = B0<<24|B1<<16|B2<<8|B3
-    const __m256i sh = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
-                                        12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i up = _mm256_and_si256(_mm256_shuffle_epi8(x, rev), _mm256_set1_epi8(char(0xDF)));
+    const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(tbl, up), up);
+    const __m256i code = _mm256_and_si256(_mm256_shuffle_epi8(ctb, up), ok);
+    // reversed order: the byte at the higher address is the EARLIER base, so it takes the higher weight
+    const __m256i p2 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));      // b_early*4 + b_late
+    const __m256i p4 = _mm256_madd_epi16(p2, _mm256_set1_epi32(0x00100001));       // early pair*16 + late pair
+    // dword d of a lane = bases 12-4d .. 15-4d of the lane: their low bytes, in order, are the little-endian word
+    const __m256i sh = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                        0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     const __m256i pk = _mm256_shuffle_epi8(p4, sh);
     const uint32_t w0 = uint32_t(_mm256_extract_epi32(pk, 0));     // bases 0..15
     const uint32_t w1 = uint32_t(_mm256_extract_epi32(pk, 4));     // bases 16..31
     codes = (uint64_t(w0) << 32) | w1;
-    // first base in the top bit: reverse the 32 bytes, then one mask bit per byte
-    const __m256i rv = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
-                                        15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
-    const __m256i okr = _mm256_permute4x64_epi64(_mm256_shuffle_epi8(ok, rv), 0x4E);
-    amb = ~uint32_t(_mm256_movemask_epi8(okr));
+    // mask bit 16L+b = base 16L+15-b; wanted: base p at bit 31-p  ->  swap the halves
+    const uint32_t m = ~uint32_t(_mm256_movemask_epi8(ok));
+    amb = (m << 16) | (m >> 16);
 }
 #endif
 
@@ -111,6 +117,7 @@ void append_avx2 (const uint8_t* s, uint64_t n, uint64_t pos, uint32_t* codes, u
     uint64_t i = 0;
     for (; i + 32 <= n; i += 32) {
         uint64_t c; uint32_t a;
+        if ((i & 32u) == 0) _mm_prefetch(reinterpret_cast<const char*>(s + i + kPrefetchAhead), _MM_HINT_T0);
         pack32_avx2(s + i, c, a);
         pl.put(c, a);
     }
@@ -125,59 +132,58 @@ void append_avx2 (const uint8_t* s, uint64_t n, uint64_t pos, uint32_t* codes, u
     pl.finish();
 }
 
-// 64 bases per iteration with AVX-512 (F + BW): one mask compare for the validity, one narrowing move for
-// the packing.  The tail (< 64 bases) goes through the AVX2 code.
-__attribute__((target("avx512f,avx512bw")))
-inline void pack64_avx512 (const uint8_t* s, uint64_t& c0, uint64_t& c1, uint32_t& a0, uint32_t& a1) {
-    const char X = 0x20;
-    const __m512i x  = _mm512_loadu_si512(reinterpret_cast<const void*>(s));
-    const __m512i up = _mm512_and_si512(x, _mm512_set1_epi8(char(0xDF)));
-    const __m512i tbl = _mm512_broadcast_i32x4(_mm_setr_epi8(X, 'A', X, 'C', 'T', 'U', X, 'G', X, X, X, X, X, X, X, X));
-    const __m512i expect = _mm512_shuffle_epi8(tbl, _mm512_and_si512(up, _mm512_set1_epi8(0x0F)));
-    const __mmask64 ok = _mm512_cmpeq_epi8_mask(expect, up);
-    const __m512i v  = _mm512_and_si512(_mm512_srli_epi16(up, 1), _mm512_set1_epi8(3));
-    __m512i code     = _mm512_xor_si512(v, _mm512_and_si512(_mm512_srli_epi16(v, 1), _mm512_set1_epi8(1)));
-    code = _mm512_maskz_mov_epi8(ok, code);
-    const __m512i p2 = _mm512_maddubs_epi16(code, _mm512_set1_epi16(0x0104));       // b0*4 + b1
-    const __m512i p4 = _mm512_madd_epi16(p2, _mm512_set1_epi32(0x00010010));        // lo*16 + hi: one byte per 4 bases
-    const __m128i b  = _mm512_cvtepi32_epi8(p4);                                     // byte i = bases 4i .. 4i+3
-    const __m128i w  = _mm_shuffle_epi8(b, _mm_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12));
-    const uint64_t q0 = uint64_t(_mm_cvtsi128_si64(w)), q1 = uint64_t(_mm_extract_epi64(w, 1));
-    c0 = (q0 << 32) | (q0 >> 32);                                                   // first 16 bases in the upper word
-    c1 = (q1 << 32) | (q1 >> 32);
-    auto rev32 = [] (uint32_t a) {
-        a = ((a >> 1) & 0x55555555u) | ((a & 0x55555555u) << 1);
-        a = ((a >> 2) & 0x33333333u) | ((a & 0x33333333u) << 2);
-        a = ((a >> 4) & 0x0F0F0F0Fu) | ((a & 0x0F0F0F0Fu) << 4);
-        return __builtin_bswap32(a);
-    };
-    const uint64_t amb = ~uint64_t(ok);                                             // bit i = base i
-    a0 = rev32(uint32_t(amb));
-    a1 = rev32(uint32_t(amb >> 32));
+// 64 bases per iteration with AVX-512 (F + BW): ~15 instructions (one mask compare for the validity, one
+// masked table lookup for the codes, two multiply-adds and one narrowing move for the packing).
+// `keep` = the bases that exist (a partial last group is loaded masked).
+// w = four code words (bases 0-15 | 16-31 | 32-47 | 48-63), a0 / a1 = ambiguity words of the two halves.
+template <bool kWhole>
+__attribute__((target("avx512f,avx512bw,avx2")))
+inline void pack64_avx512 (const uint8_t* s, __mmask64 keep, __m128i& w, uint32_t& a0, uint32_t& a1) {
+    MCB_PACK_TABLES(_mm512_broadcast_i32x4);
+    const __m512i x  = kWhole ? _mm512_loadu_si512(reinterpret_cast<const void*>(s))
+                              : _mm512_maskz_loadu_epi8(keep, reinterpret_cast<const void*>(s));
+    const __m512i up = _mm512_and_si512(_mm512_shuffle_epi8(x, rev), _mm512_set1_epi8(char(0xDF)));
+    const __mmask64 ok = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tbl, up), up);
+    const __m512i code = _mm512_maskz_shuffle_epi8(ok, ctb, up);
+    const __m512i p2 = _mm512_maddubs_epi16(code, _mm512_set1_epi16(0x0401));
+    const __m512i p4 = _mm512_madd_epi16(p2, _mm512_set1_epi32(0x00100001));
+    w = _mm512_cvtepi32_epi8(p4);                                   // dword j = bases 16(j/4) + 12-4(j%4) ..+3
+    // `ok` is in lane-reversed order; `keep` is in memory order: bring the validity to memory order per half
+    const uint64_t bad = ~uint64_t(ok);
+    const uint32_t lo = uint32_t(bad), hi = uint32_t(bad >> 32);
+    a0 = (lo << 16) | (lo >> 16);
+    a1 = (hi << 16) | (hi >> 16);
 }
+
+// bit p of the result = 1 for the first n of 32 bases, first base in the top bit
+inline uint32_t head_bits (uint32_t n) { return n >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> n); }
 
 __attribute__((target("avx512f,avx512bw,avx2")))
 void append_avx512 (const uint8_t* s, uint64_t n, uint64_t pos, uint32_t* codes, uint32_t* amb) {
-    Placer pl(codes, amb, pos);
     uint64_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        uint64_t c0, c1; uint32_t a0, a1;
-        pack64_avx512(s + i, c0, c1, a0, a1);
-        pl.put(c0, a0);
-        pl.put(c1, a1);
+    if ((pos & 31u) == 0) {
+        // word-aligned start (the bulk path of mcb200_batch_add_reads): whole groups are stored as they come
+        uint32_t* c = codes + 2 * (pos >> 5);
+        uint32_t* a = amb + (pos >> 5);
+        for (; i + 64 <= n; i += 64) {
+            __m128i w; uint32_t a0, a1;
+            _mm_prefetch(reinterpret_cast<const char*>(s + i + kPrefetchAhead), _MM_HINT_T0);
+            pack64_avx512<true>(s + i, ~__mmask64(0), w, a0, a1);
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(c + i / 16), w);
+            a[i / 32] = a0; a[i / 32 + 1] = a1;
+        }
     }
-    for (; i + 32 <= n; i += 32) {
-        uint64_t c; uint32_t a;
-        pack32_avx2(s + i, c, a);
-        pl.put(c, a);
-    }
-    if (i < n) {
-        alignas(32) uint8_t tmp[32];
-        memset(tmp, 'A', 32);
-        memcpy(tmp, s + i, n - i);
-        uint64_t c; uint32_t a;
-        pack32_avx2(tmp, c, a);
-        pl.put(c, a);
+    Placer pl(codes, amb, pos + i);
+    for (; i < n; i += 64) {
+        const uint64_t m = n - i;
+        const __mmask64 keep = m >= 64 ? ~__mmask64(0) : ((__mmask64(1) << m) - 1);
+        __m128i w; uint32_t a0, a1;
+        if (m >= 64) _mm_prefetch(reinterpret_cast<const char*>(s + i + kPrefetchAhead), _MM_HINT_T0);
+        pack64_avx512<false>(s + i, keep, w, a0, a1);
+        const uint64_t q0 = uint64_t(_mm_cvtsi128_si64(w)), q1 = uint64_t(_mm_extract_epi64(w, 1));
+        // bases that do not exist were loaded as 0: code 0 already, ambiguity bit cleared here (the zero tail)
+        pl.put((q0 << 32) | (q0 >> 32), a0 & head_bits(uint32_t(m < 32 ? m : 32)));
+        if (m > 32) pl.put((q1 << 32) | (q1 >> 32), a1 & head_bits(uint32_t(m - 32 < 32 ? m - 32 : 32)));
     }
     pl.finish();
 }
@@ -209,7 +215,7 @@ extern "C" void mcb200_internal_pack_append (const char* bases, uint64_t n, uint
 #ifdef MCB_X86
     // force_scalar: 0 = best available, 1 = scalar, 2 = at most AVX2 (tests)
     const int level = force_scalar == 1 ? 0 : (force_scalar == 2 ? (mcb200_internal_pack_has_avx2() ? 1 : 0) : mcb200_internal_pack_has_avx2());
-    if (level == 2 && n >= 64) { append_avx512(s, n, pos, codes, amb); return; }
+    if (level == 2) { append_avx512(s, n, pos, codes, amb); return; }
     if (level >= 1) { append_avx2(s, n, pos, codes, amb); return; }
 #endif
     append_scalar(s, n, pos, codes, amb);

@@ -65,6 +65,23 @@ def test_appends_at_every_offset_match_the_layout(force_scalar):
         assert np.array_equal(amb, ra), (trial, lens)
 
 
+@pytest.mark.parametrize("force_scalar", [1, 2, 0])
+def test_long_appends_of_arbitrary_bytes_at_aligned_and_odd_positions(force_scalar):
+    """the bulk path (whole 64-base groups stored directly when the append starts on a word) and the
+    shifted path, over every byte value incl. >= 0x80, with every tail length"""
+    rng = np.random.default_rng(23)
+    for trial, (first, n) in enumerate([(0, 70000), (32, 4096 + 63), (64, 129), (5, 65536 + 17), (31, 1000), (33, 64),
+                                        (0, 64), (0, 63), (0, 65), (96, 127), (7, 191)]):
+        body = rng.integers(0, 256, size=n).astype(np.uint8)
+        mostly = ALPHABET[rng.integers(0, 8, size=n)]
+        body = np.where(rng.random(n) < 0.9, mostly, body).astype(np.uint8)
+        chunks = [ALPHABET[rng.integers(0, 8, size=first)], body, ALPHABET[rng.integers(0, 8, size=trial)]]
+        codes, amb = pack_lib(chunks, force_scalar)
+        rc, ra = pack_numpy(np.concatenate(chunks))
+        assert np.array_equal(codes, rc), (first, n)
+        assert np.array_equal(amb, ra), (first, n)
+
+
 def test_one_bulk_append_equals_read_by_read():
     rng = np.random.default_rng(11)
     chunks = [ALPHABET[rng.integers(0, 10, size=150)] for _ in range(500)]
