@@ -89,3 +89,22 @@ def need_c1(gpu_test=False):
         pytest.fail("oracle/_ref/c1 is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
                     "/root/reference exists (the parity test against the reference's golden file must not vanish)")
     pytest.skip("oracle/_ref/c1 not built and no reference sources here")
+
+
+def reference_abundance_blocks(path):
+    """the `-abundances -abundance-per <rank>` tables in a captured output of the reference CLI: one list of
+    lines per queried input (header lines, rows, the `unclassified` row; both tables)"""
+    blocks, cur = [], None
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith("# query summary: number of queries mapped per taxon"):
+            cur = [line]
+            blocks.append(cur)
+        elif cur is not None:
+            if line.startswith("# ") and not (line.startswith("# rank:name") or line.startswith("# estimated abundance")):
+                cur = None
+            elif "\t|\t" in line or line.startswith("# "):
+                cur.append(line)
+                if line.startswith("unclassified") and any(x.startswith("# estimated") for x in cur):
+                    cur = None
+    return blocks

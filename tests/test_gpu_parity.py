@@ -221,10 +221,23 @@ def test_c1_bundled_database_matches_reference_golden_file():
         "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)],
         "pair.1 + data/pair.2": [(a[1], b[1]) for a, b in zip(p1, p2)],
     }
+    from metacache_b200.statistics import ClassificationStatistics, TaxonCounts
+    from tests.golden_util import reference_abundance_blocks
+    blocks = reference_abundance_blocks(os.path.join(C1, "cli_cpu_reference.out"))
+    assert len(blocks) == len(runs)
     total = classified = 0
-    for sec, items in runs.items():
+    for si, (sec, items) in enumerate(runs.items()):
         exp = expected[sec]
         res = query_reads(db, items, copy_all_hits=True, classify=True)
+        # -abundances -abundance-per species from the DEVICE's classifications (test/run_tests:153), against
+        # what the unmodified CPU reference prints (estimate_abundance, classification.cpp:304-377)
+        pairs = np.asarray([r[2] for r in res], np.uint32).reshape(-1, 2)
+        st, tc = ClassificationStatistics(), TaxonCounts(db.meta.taxa)
+        st.assign_batch(pairs)
+        tc.count_batch(pairs)
+        lines = tc.abundance_lines(st)
+        tc.estimate_abundance(4)
+        assert lines + tc.estimate_lines(st, 4) == blocks[si], sec
         for qid, (allh, top, cls) in enumerate(res, start=1):
             if qid not in exp:
                 continue

@@ -125,7 +125,7 @@ def test_oracle_classification_matches_reference_golden_file():
     need_c1()
     from metacache_b200 import dbformat, formatting
     from metacache_b200.database import Database
-    from metacache_b200.statistics import ClassificationStatistics
+    from metacache_b200.statistics import ClassificationStatistics, TaxonCounts
     from oracle import refio
     meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
     c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
@@ -147,7 +147,7 @@ def test_oracle_classification_matches_reference_golden_file():
     runs = {"single": [(s, b"") for _, s in single],
             "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)]}
     classified = 0
-    summaries = {}
+    summaries, abundances = {}, {}
     for sec, items in runs.items():
         cls = []
         for qid, (a, b) in enumerate(items, start=1):
@@ -160,6 +160,16 @@ def test_oracle_classification_matches_reference_golden_file():
         st = ClassificationStatistics()
         st.assign_batch(np.asarray(cls, np.uint32))
         summaries[sec] = st.summary_lines()
+        # -abundances -abundance-per species (test/run_tests:153): per-taxon counts, then the estimate
+        tc = TaxonCounts(meta.taxa)
+        half = len(cls) // 2                                        # two workers' maps merged = one map
+        tc.count_batch(np.asarray(cls[:half], np.uint32))
+        other = TaxonCounts(meta.taxa)
+        other.count_batch(np.asarray(cls[half:], np.uint32))
+        tc.merge(other)
+        lines = tc.abundance_lines(st)
+        tc.estimate_abundance(4)
+        abundances[sec] = lines + tc.estimate_lines(st, 4)
     assert classified > 150
     # the per-rank summary block the reference prints after each section (show_taxon_statistics)
     want, section = {}, None
@@ -172,6 +182,16 @@ def test_oracle_classification_matches_reference_golden_file():
     for sec in runs:
         key = next(k for k in want if k.startswith(sec))
         assert summaries[sec] == want[key], sec
+    # the abundance tables, against what the unmodified CPU reference prints for its own CLI test
+    # (oracle/_ref/c1/cli_cpu_reference.out; upstream's classified.expected predates a change of these rows)
+    from tests.golden_util import reference_abundance_blocks
+    blocks = reference_abundance_blocks(os.path.join(C1, "cli_cpu_reference.out"))
+    assert len(blocks) == 3                                        # single, -pairseq, -pairfiles
+    assert abundances["single"] == blocks[0]
+    assert abundances["pairs"] == blocks[1]
+    est = blocks[0][blocks[0].index("# estimated abundance (number of queries) per species"):]
+    species = [x.split("\t|\t") for x in est if x.startswith("species:")]
+    assert len(species) >= 3 and any("." in x[2] for x in species)   # the proportional split is exercised
 
 
 @pytest.mark.parametrize("gi", range(5))
