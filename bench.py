@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--target-len", type=int, default=100_000)
     ap.add_argument("--slot-reads", type=int, default=125_000, help="reads per host batch slot (e2e)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host worker threads of the e2e run (0 = one per core, max 32)")
+    ap.add_argument("--e2e-slots-per-worker", type=int, default=3, help="batch slots each e2e worker rotates through (one being filled, the others in flight)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end measurement (kernel experiments only)")
@@ -323,7 +324,8 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     T = max(1, min((os.cpu_count() or 1) // max(1, args.gpus), args.e2e_threads or 32))    # the ranks of a box share its cores
     per = min(args.slot_reads, (nq + T - 1) // T)
     chunks = [(c, min(c + per, nq)) for c in range(0, nq, per)]
-    nslots = 3 * T
+    SPW = max(2, args.e2e_slots_per_worker)                    # slots per worker: fill one while the others are in flight
+    nslots = SPW * T
     slot_bases = max(int(host_offs[e] - host_offs[b]) for b, e in chunks)
     qb = _lib.check_ptr(L.mcb200_batch_create(db._h, per, slot_bases + 64, MAXC, 0, nslots))
     tops = np.zeros((nq, MAXC, 4), np.uint32)
@@ -334,7 +336,6 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     errors = []
     spent = [[0.0, 0.0, 0.0] for _ in range(T)]               # per worker: wait + collect | add (pack) | submit
 
-    SPW = 3                                                    # slots per worker: fill one while two are in flight
     verify_n = min(len(top_first), nq) if top_first is not None else 0
 
     def collect(slot, ci):
@@ -442,7 +443,7 @@ def e2e_host_buffers(args, L, db, sk, host_reads, host_offs, nq, top_first, devi
     L.mcb200_batch_destroy(qb)
     return {"value": nq / (wall_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": round(wall_ms, 3), "timed_by": "wall clock, host work included",
-            "host_threads": T, "slots": nslots, "reads_per_slot": per, "host_ms_per_thread_per_step": host_ms,
+            "host_threads": T, "slots": nslots, "slots_per_worker": SPW, "reads_per_slot": per, "host_ms_per_thread_per_step": host_ms,
             "chunks": "taken one by one by whichever worker is free",
             "packer": ("scalar", "avx2", "avx512")[int(L.mcb200_internal_pack_has_avx2())],
             "results_equal_device_resident_path": same,
