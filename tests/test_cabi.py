@@ -66,3 +66,19 @@ def test_product_path_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "mc_oracle" not in txt.replace(
                     "oracle/mc_oracle.c:top_insert", ""), f
+
+
+def test_loading_the_library_defaults_the_stream_channels_without_overriding_the_host():
+    """the batch slots run on one stream each; the library raises CUDA_DEVICE_MAX_CONNECTIONS (8 by default,
+    streams sharing a channel serialise) when it is loaded, unless the host program set it (api.cu)"""
+    import sys
+    code = ("import ctypes\nfrom metacache_b200 import _lib\n_lib.lib()\n"
+            "g = ctypes.CDLL(None).getenv\ng.restype = ctypes.c_char_p\n"
+            "print(g(b'CUDA_DEVICE_MAX_CONNECTIONS').decode())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for preset, want in ((None, "32"), ("4", "4")):
+        env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+        if preset:
+            env["CUDA_DEVICE_MAX_CONNECTIONS"] = preset
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, check=True)
+        assert out.stdout.strip() == want
