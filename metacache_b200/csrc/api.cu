@@ -727,6 +727,7 @@ struct mcb200_workspace {
     mcb200_dev_queries q{};
     SketchParams sk{16, 16, 127, 112};
     uint64_t win_bound = 0;
+    uint64_t win_alloc = 0;                     // windows the sketch buffers are allocated for (capacity, see sketch_impl)
     bool sketched = false;
     cudaStream_t last_stream = nullptr;
 
@@ -905,8 +906,15 @@ static int sketch_impl (mcb200_workspace* ws, const mcb200_dev_queries* q, const
     const uint64_t bound = q->n_bases / sk->winstride + 2ull * q->n_seqs;
     if (bound * sk->sketchlen >= (1ull << 32)) return fail(MCB200_EINVAL, "too many windows for one call; split the batch");
     ws->win_bound = bound;
-    CU(ws->win_seq.ensure(bound));
-    CU(ws->feats.ensure(bound * sk->sketchlen));
+    // Allocate for the CAPACITY of the workspace, not for this batch: a slot that is refilled with batches of
+    // varying size (long reads; any streaming host) would otherwise grow its buffers again and again, and
+    // every cudaFree / cudaMalloc synchronises the whole device under the other slots in flight (C3 end to
+    // end: submit 73 ms per worker and step).  A full batch needs the same room, so nothing extra is claimed.
+    uint64_t alloc = ws->max_bases / sk->winstride + 2ull * ws->max_seqs;
+    if (alloc < bound || alloc * sk->sketchlen >= (1ull << 32)) alloc = bound;
+    ws->win_alloc = alloc;
+    CU(ws->win_seq.ensure(alloc));
+    CU(ws->feats.ensure(alloc * sk->sketchlen));
 
     if (ws->profiling) { int rc2 = next_event_set(ws); if (rc2) return rc2; CU(cudaEventRecord(ws->ev->sk[0], st)); }
     if (!packed) { launch_encode(q->bases, q->n_bases, ws->codes.p, ws->amb.p, st); d_codes = ws->codes.p; d_amb = ws->amb.p; }
@@ -1058,9 +1066,10 @@ static int remote_query (mcb200_workspace* ws, uint32_t child, uint32_t local_pa
     int rc = 0;
     cudaError_t e = cudaStreamWaitEvent(r->own_stream, ws->ev_sketched, 0);
     const uint64_t nfeat = ws->win_bound * s;
-    if (e == cudaSuccess) e = r->feats.ensure(nfeat);
-    if (e == cudaSuccess) e = r->r_max_win.ensure(nq);
-    if (e == cudaSuccess) e = r->r_top.ensure(uint64_t(nq) * ws->maxc);
+    // (allocated for the home workspace's capacity, as its own buffers are: no regrowth from batch to batch)
+    if (e == cudaSuccess) e = r->feats.ensure(std::max<uint64_t>(nfeat, ws->win_alloc * s));
+    if (e == cudaSuccess) e = r->r_max_win.ensure(std::max<uint64_t>(nq, ws->max_queries));
+    if (e == cudaSuccess) e = r->r_top.ensure(uint64_t(std::max<uint64_t>(nq, ws->max_queries)) * ws->maxc);
     // (the window bound, not the window count, is known without a synchronisation)
     if (e == cudaSuccess) e = cudaMemcpyPeerAsync(r->feats.p, rdev, ws->feats.p, hdev, nfeat * 4, r->own_stream);
     if (e == cudaSuccess) e = cudaMemcpyPeerAsync(r->qry_win_off.p, rdev, ws->qry_win_off.p, hdev, (uint64_t(nq) + 1) * 4, r->own_stream);
