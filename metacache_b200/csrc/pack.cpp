@@ -13,7 +13,7 @@
 // read may start at any bit offset.  Words are completed by later appends: an append ORs into the
 // partially filled word it starts in and STORES every further word (tail bits zero), which needs
 // no pre-cleared memory.  AVX-512 (F+BW) or AVX2 when the CPU has them (runtime dispatch), scalar otherwise;
-// with AVX-512 one core packs ~23 GB/s of ASCII from its cache and ~9 GB/s from memory (the source is
+// with AVX-512 one core packs ~24 GB/s of ASCII from its cache and ~8 GB/s from memory (the source is
 // prefetched in software, see kPrefetchAhead), ~12 / ~7 GB/s with AVX2.
 #include <cstdint>
 #include <cstring>
@@ -42,8 +42,9 @@ inline void pack32_scalar (const uint8_t* s, uint32_t n, uint64_t& codes, uint32
 
 #ifdef MCB_X86
 // how far ahead of the loads the source is prefetched: the loop is a pure stream, and under a hypervisor
-// the hardware prefetchers alone leave a core at a third of its read rate (measured: 3.8 -> 9.3 GB/s per
-// core, 17 -> 45 GB/s on 8 cores; 1.5 - 2 KB ahead is the flat optimum)
+// the hardware prefetchers alone leave a streaming core well below its read rate (measured with the old packer:
+// 3.8 -> 6.0 GB/s per core and 17 -> 34 GB/s on 8 cores from the prefetch alone; 1.5 - 2 KB ahead is the flat
+// optimum; profiles/pack_bench_r2.txt has the before / after of the whole rewrite)
 constexpr uint64_t kPrefetchAhead = 1536;
 
 // The vector paths reverse the bytes of every 16-byte lane FIRST.  The multiply-adds then leave "first base
