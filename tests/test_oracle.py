@@ -212,3 +212,38 @@ def test_oracle_matches_reference_for_other_geometries(gi):
         allh, top = O.query(tab, a, b, k, s, w, stride, maxc=2)
         assert np.array_equal(allh, exp.allhits[i]), i
         assert top == exp.top[i], i
+
+
+def test_abundance_estimates_at_every_rank_match_the_reference_cli():
+    """`-abundances -abundance-per <rank>` for eight ranks from sequence to domain: the tables of
+    tests/golden/abundance.json were printed by the unmodified CPU reference (oracle/make_abundance_golden.py);
+    here the classifications come from the oracle and the tables from metacache_b200.statistics"""
+    need_c1()
+    import json
+    from metacache_b200 import dbformat
+    from metacache_b200.database import Database
+    from metacache_b200.formatting import RANK_NAMES
+    from metacache_b200.statistics import ClassificationStatistics, TaxonCounts
+    from oracle import refio
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "abundance.json")))["blocks"]
+    meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
+    c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
+    tab = O.Table(c.keys, c.sizes, c.values)
+    db = Database.__new__(Database)
+    db.meta = meta
+    lin = Database.target_lineages(db)
+    single = refio.read_fasta(os.path.join(C1, "single.fa"))
+    pf = refio.read_fasta(os.path.join(C1, "pairs.fa"))
+    runs = {"single": [(s, b"") for _, s in single],
+            "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)]}
+    for sec, items in runs.items():
+        cls = np.asarray([O.classify(O.query(tab, a, b)[1], lin, hits_min=5) for a, b in items], np.uint32)
+        st = ClassificationStatistics()
+        st.assign_batch(cls)
+        for rank_name, blocks in gold.items():
+            rank = RANK_NAMES.index(rank_name)
+            tc = TaxonCounts(meta.taxa)
+            tc.count_batch(cls)
+            lines = tc.abundance_lines(st)
+            tc.estimate_abundance(rank)
+            assert lines + tc.estimate_lines(st, rank) == blocks[sec], (sec, rank_name)
