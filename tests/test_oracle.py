@@ -247,3 +247,49 @@ def test_abundance_estimates_at_every_rank_match_the_reference_cli():
             lines = tc.abundance_lines(st)
             tc.estimate_abundance(rank)
             assert lines + tc.estimate_lines(st, rank) == blocks[sec], (sec, rank_name)
+
+
+def test_oracle_candidates_and_classification_under_other_options_match_the_reference_cli():
+    """-hitmin / -hitdiff / -maxcand / -lowest / -highest away from their defaults: top_hits and classification
+    columns printed by the unmodified CPU reference for its own test reads (tests/golden/classify_options.json,
+    oracle/make_classify_golden.py) against the oracle's candidates (taxon merge below `lowest`,
+    candidate_generation.hpp:172-231) and classify() (classification.cpp:146-189)"""
+    need_c1()
+    import json
+    from metacache_b200 import dbformat, formatting
+    from metacache_b200.database import Database
+    from oracle import refio
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "classify_options.json")))["sets"]
+    meta = dbformat.read_meta(os.path.join(C1, "bacteria1.meta"))
+    c = dbformat.read_cache(os.path.join(C1, "bacteria1.cache0"))
+    tab = O.Table(c.keys, c.sizes, c.values)
+    db = Database.__new__(Database)
+    db.meta = meta
+    lin = Database.target_lineages(db)
+    names = meta.target_names()
+    single = refio.read_fasta(os.path.join(C1, "single.fa"))
+    pf = refio.read_fasta(os.path.join(C1, "pairs.fa"))
+    runs = {"single": [(s, b"") for _, s in single],
+            "pairs": [(pf[i][1], pf[i + 1][1]) for i in range(0, len(pf), 2)]}
+    for name, g in gold.items():
+        p = g["params"]
+        keys = Database.ranked_lineage_keys(db, p["lowest"]) if p["lowest"] > 0 else None
+        seen = 0
+        for sec, items in runs.items():
+            rows = g["reads"][sec]
+            for qid, (a, b) in enumerate(items, start=1):
+                top = O.query(tab, a, b, maxc=p["maxc"], tax_of_tgt=keys)[1]
+                t, r = O.classify(top, lin, hits_min=p["hits_min"], hits_diff_fraction=p["frac"],
+                                  lowest=p["lowest"], highest=p["highest"])
+                want = rows.get(str(qid))
+                if want is None:
+                    assert t == 0, (name, sec, qid, top)                      # -mapped-only: not printed = not classified
+                    continue
+                seen += 1
+                if keys is None:
+                    got_top = formatting.format_top_hits(top, names)
+                else:                                                         # show_candidates above sequence: taxid:hits
+                    got_top = ",".join(f"{int(np.int64(keys[tgt]))}:{hits}" for tgt, hits, _b, _e in top if hits > 0)
+                assert got_top == want[0], (name, sec, qid)
+                assert formatting.format_classification(t, r, meta.taxa) == want[1], (name, sec, qid, top)
+        assert seen == sum(len(v) for v in g["reads"].values()), name
